@@ -1,0 +1,166 @@
+/* pg_b200 — C ABI of the B200-native PaliGemma hot path.
+ *
+ * The reference (PhilipWilliamVentura/multimodal-financial-analysis-tool-using-paligemma)
+ * is pure Python/PyTorch and has no FFI of its own: its boundary is the
+ * Python class surface of modeling_gemma.py / modeling_siglip.py.  Our drop-in modules of
+ * the same names call these entry points (ctypes); every entry names
+ * the reference code it replaces.
+ *
+ * Conventions: plain device pointers and sizes, no torch types; `stream` is a
+ * cudaStream_t passed as void*; every call is asynchronous on that stream, allocates
+ * nothing and never synchronises; return 0 on success, non-zero otherwise with a message
+ * in pg_last_error().  `dtype` selects the model dtype of activations and weights
+ * (PG_F32 is the fp32 verification mode: true fp32 FMA, no TF32).  Matrices are row-major;
+ * weights are [out_features, in_features] exactly as torch.nn.Linear stores them.
+ */
+#ifndef PG_B200_H
+#define PG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { PG_F32 = 0, PG_BF16 = 1, PG_F16 = 2 };
+enum { PG_OK = 0, PG_ERR_INVALID = 1, PG_ERR_CUDA = 2 };
+
+/* pg_gemm epilogues (all round to the model dtype where the reference materialises a tensor) */
+enum {
+  PG_EPI_NONE = 0,      /* C = A W^T                                  */
+  PG_EPI_BIAS = 1,      /* C = A W^T + b                  nn.Linear   */
+  PG_EPI_BIAS_GELU = 2, /* C = gelu_tanh(A W^T + b)       SiglipMLP fc1 */
+  PG_EPI_BIAS_RES = 3,  /* C = (A W^T + b) + R            out_proj / fc2 / patch-embed+pos */
+  PG_EPI_RES = 4,       /* C = (A W^T) + R                o_proj / down_proj */
+  PG_EPI_GEGLU = 5      /* C = gelu_tanh(A Wg^T) * (A Wu^T), W = [Wg; Wu]  GemmaMLP */
+};
+
+const char* pg_last_error(void);
+int pg_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+unsigned long long pg_launch_count(void);
+
+/* ---- embedding + image/text merge + sqrt(D) normaliser --------------------------------
+ * Replaces nn.Embedding lookup (modeling_gemma.py:565), _merge_input_ids_with_image_features
+ * (:476-500) and the `hidden_states * normalizer` of GemmaModel.forward (:367-368).
+ * out[t] = 0 for pad ids; rnd(rnd(img[k]/img_div) * normalizer) for the k-th image token in
+ * row-major order; rnd(emb[id] * normalizer) otherwise.  ids may be int64 device memory.
+ * If an image token has no image row left (reference: masked_scatter raises) or an id is out
+ * of range, *err_flag (device int, may be NULL) is set to 1 and the row is zero. */
+int pg_embed_merge(void* out, const int64_t* ids, const void* emb, const void* img_feats,
+                   int n_tokens, int D, int64_t vocab, int64_t image_token_id, int64_t pad_id,
+                   int n_img_rows, float img_div, float normalizer, int* err_flag,
+                   int dtype, void* stream);
+
+/* GemmaRMSNorm.forward (modeling_gemma.py:114-120) */
+int pg_rmsnorm(void* out, const void* x, const void* w, int rows, int D, float eps,
+               int dtype, void* stream);
+/* nn.LayerNorm (modeling_siglip.py:175,177,234) */
+int pg_layernorm(void* out, const void* x, const void* w, const void* b, int rows, int D,
+                 float eps, int dtype, void* stream);
+
+/* SiglipVisionEmbeddings patch conv as im2col (modeling_siglip.py:45-51,67-73): stride == kernel
+ * so it is a pure permutation: out[(b*P + py*G + px), c*p*p + ky*p + kx], row stride ld_out
+ * (columns beyond C*p*p are zero-filled up to ld_out). */
+int pg_im2col(void* out, const void* pixels, int B, int C, int H, int W, int p, int ld_out,
+              int dtype, void* stream);
+
+/* C[M,N] = A[M,K] W[N,K]^T with a fused epilogue; fp32 accumulation.  R row index is
+ * m % res_mod when res_mod > 0 (position-embedding broadcast over the batch).  out_f32 != 0
+ * stores fp32 (lm_head `.float()`, modeling_gemma.py:417-418).  impl: 0 = auto, 1 = SIMT
+ * (any dtype), 2 = tcgen05/TMA (bf16/f16 only).  Replaces every nn.Linear / matmul call site
+ * of SURVEY.md §2.3 on the prefill and vision paths. */
+int pg_gemm(void* C, const void* A, const void* W, const void* bias, const void* R,
+            int M, int N, int K, int lda, int ldw, int ldc, int ldr, int res_mod,
+            int epilogue, int out_f32, int impl, int dtype, void* stream);
+
+/* RoPE on q and k + append of K,V to the paged cache (modeling_gemma.py:155-199, 23-36).
+ * qkv: [B*q_len, (nq+2*nkv)*hd] from the fused projection; q_out: [B*q_len, nq*hd].
+ * Token (b,i) gets position positions[b*q_len+i] (clamped to [0,max_pos-1]) and cache slot
+ * slot_base[b]+i.  Pools are [num_pages, page_size, nkv*hd]. */
+int pg_rope_append(void* q_out, const void* qkv, const float* inv_freq, const int32_t* positions,
+                   void* k_pool, void* v_pool, const int32_t* page_table, int pt_stride,
+                   int page_size, const int32_t* slot_base, int B, int q_len, int nq, int nkv,
+                   int hd, int max_pos, int dtype, void* stream);
+
+/* Unmasked softmax attention (the reference's additive mask is all zeros: modeling_gemma.py:
+ * 506-514; SigLIP has none: modeling_siglip.py:116-131).  fp32 softmax.  q: [B*q_len, ld_q],
+ * head h at column h*hd.  K/V either contiguous (page_table NULL: row (b,j) at
+ * base + b*kv_batch_stride + j*ld_kv elements) or paged.  kv_len: device int32[B] or NULL
+ * (then kv_len_const).  kv_len_add is added to the device value.  scale_mode 0: s*scale
+ * (SigLIP), 1: s/scale (Gemma). */
+int pg_attention(void* out, int ld_out, const void* q, int ld_q, const void* k, const void* v,
+                 int ld_kv, long long kv_batch_stride, const int32_t* page_table, int pt_stride,
+                 int page_size, const int32_t* kv_len, int kv_len_const, int kv_len_add, int B,
+                 int q_len, int n_heads, int n_kv_heads, int hd, float scale, int scale_mode,
+                 int dtype, void* stream);
+
+/* ---- decode path (q_len == 1 per sequence), B <= PG_MAX_DECODE_BATCH per call ----------- */
+#define PG_MAX_DECODE_BATCH 8
+
+/* input RMSNorm + fused q/k/v projection + RoPE + KV append (GemmaDecoderLayer.forward
+ * :314-316, GemmaAttention.forward :241-259).  x: [B,D] residual stream. positions/kv_len:
+ * device int32[B]; K,V go to slot kv_len[b]. */
+int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_qkv,
+                  const float* inv_freq, const int32_t* positions, void* k_pool, void* v_pool,
+                  const int32_t* page_table, int pt_stride, int page_size, const int32_t* kv_len,
+                  int B, int D, int nq, int nkv, int hd, float eps, int max_pos, int dtype,
+                  void* stream);
+
+/* split-K MQA attention over the paged cache for one new token per sequence
+ * (modeling_gemma.py:262-288).  Attends kv_len[b]+kv_len_add entries.  ws: fp32 workspace of
+ * pg_decode_attention_ws_floats() floats; counters: int32[B*nkv], zero before first use. */
+long long pg_decode_attention_ws_floats(int B, int nq, int hd, int max_splits);
+int pg_decode_attention(void* out, const void* q, const void* k_pool, const void* v_pool,
+                        const int32_t* page_table, int pt_stride, int page_size,
+                        const int32_t* kv_len, int kv_len_add, int B, int nq, int nkv, int hd,
+                        float scale_div, float* ws, int* counters, int max_splits, int dtype,
+                        void* stream);
+
+/* out[B,N] = (x[B,K] W[N,K]^T) + R  — o_proj / down_proj with the residual add
+ * (modeling_gemma.py:291,327 and :134,336).  R may be NULL. */
+int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, int N, int K,
+                int dtype, void* stream);
+
+/* post-attention RMSNorm + gate/up projections + GeGLU (modeling_gemma.py:332,134).
+ * w_gu = [Wgate; Wup] : [2F, D];  out: [B,F]. */
+int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w_gu, int B,
+                     int D, int F, float eps, int dtype, void* stream);
+
+/* final RMSNorm + tied lm_head + fp32 logits + greedy argmax (modeling_gemma.py:379,417-418;
+ * inference.py:68).  logits: fp32 [B,V] (values rounded to the model dtype first, as the
+ * reference's `.float()` of a model-dtype tensor).  argmax_keys: device u64[B], must hold 0
+ * on entry; decoded by pg_step_advance.  Ties go to the lowest index. */
+int pg_decode_lmhead(float* logits, const void* x, const void* norm_w, const void* w_emb,
+                     int B, int D, int64_t V, float eps, unsigned long long* argmax_keys,
+                     int dtype, void* stream);
+
+/* End of a decode step, all on device (replaces the host side of inference.py:68-78):
+ * token[b] = argmax(keys[b]) (or sampled[b] if sampled != NULL); next_ids[b] = token;
+ * history[b*hist_stride + step_counter] = token; kv_len[b] += 1; positions[b] += 1;
+ * keys[b] = 0; *step_counter += 1 (by thread 0). */
+int pg_step_advance(int64_t* next_ids, int64_t* history, int hist_stride, int* step_counter,
+                    unsigned long long* keys, const int64_t* sampled, int32_t* kv_len,
+                    int32_t* positions, int B, void* stream);
+
+/* torch.argmax(logits, -1) over fp32 [B,V] (inference.py:68).  keys_ws: device u64[B] holding 0
+ * on entry (left 0 on exit). */
+int pg_argmax(int64_t* out, const float* logits, unsigned long long* keys_ws, int B, int64_t V,
+              void* stream);
+
+/* softmax(logits/temperature) + nucleus (top-p) sampling (inference.py:15-24,65-66).
+ * The nucleus is the reference's: descending order, keep while (cumsum - p_i) <= top_p;
+ * the draw uses counter-based Philox (seed, *rng_offset + b) rather than torch's RNG stream.
+ * probs_ws: fp32 [B,V] scratch. nucleus_size (int32[B], may be NULL) reports the kept count. */
+int pg_top_p_sample(int64_t* out, const float* logits, float* probs_ws, int B, int64_t V,
+                    float temperature, float top_p, unsigned long long seed,
+                    const int* rng_offset, int* nucleus_size, void* stream);
+
+/* KVCache.key_cache[layer] / value_cache[layer] view: gather pages into a contiguous
+ * [B, nkv, T, hd] tensor (modeling_gemma.py:12-36 attribute parity). */
+int pg_kv_gather(void* out, const void* pool, const int32_t* page_table, int pt_stride,
+                 int page_size, int B, int T, int nkv, int hd, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PG_B200_H */

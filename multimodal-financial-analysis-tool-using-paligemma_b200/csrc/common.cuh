@@ -1,0 +1,156 @@
+// Shared device helpers for the pg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <type_traits>
+
+#include "../../include/pg_b200.h"
+
+namespace pg {
+
+typedef __nv_bfloat16 bf16;
+typedef __half f16;
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define PG_REQUIRE(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      pg::set_error(__VA_ARGS__);        \
+      return (int)PG_ERR_INVALID;        \
+    }                                    \
+  } while (0)
+
+// Dispatch a templated launcher on the runtime dtype enum.
+#define PG_DISPATCH_DTYPE(dtype, T, ...)                                  \
+  switch (dtype) {                                                        \
+    case PG_F32: { typedef float T; __VA_ARGS__; } break;                 \
+    case PG_BF16: { typedef pg::bf16 T; __VA_ARGS__; } break;             \
+    case PG_F16: { typedef pg::f16 T; __VA_ARGS__; } break;               \
+    default: pg::set_error("bad dtype %d", (int)(dtype)); return PG_ERR_INVALID; \
+  }
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------- scalar conversion
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<f16>(f16 v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ f16 from_f<f16>(float v) { return __float2half_rn(v); }
+
+// Round an fp32 value to the model dtype and back: the reference materialises a tensor of
+// the model dtype after every ATen op, so fused kernels round at the same points.
+template <typename T> __device__ __forceinline__ float rnd(float v) { return to_f<T>(from_f<T>(v)); }
+template <> __device__ __forceinline__ float rnd<float>(float v) { return v; }
+
+// ---------------------------------------------------------------- 16-byte vectors
+template <typename T> struct Vec;  // VEC elements of T in one 128-bit access
+template <> struct Vec<float> { static constexpr int N = 4; };
+template <> struct Vec<bf16> { static constexpr int N = 8; };
+template <> struct Vec<f16> { static constexpr int N = 8; };
+
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  // weights are read exactly once per step: bypass L1 allocation
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_cached(const void* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+template <typename T> __device__ __forceinline__ void unpack(const uint4& u, float* f);
+template <> __device__ __forceinline__ void unpack<float>(const uint4& u, float* f) {
+  f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y);
+  f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+}
+template <> __device__ __forceinline__ void unpack<bf16>(const uint4& u, float* f) {
+  // bf16 -> fp32 is a 16-bit shift
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack<f16>(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+template <typename T> __device__ __forceinline__ uint4 pack(const float* f);
+template <> __device__ __forceinline__ uint4 pack<float>(const float* f) {
+  return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+template <> __device__ __forceinline__ uint4 pack<bf16>(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+template <> __device__ __forceinline__ uint4 pack<f16>(const float* f) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum; `red` is >= 32 floats of shared memory. Every thread gets the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  return warp_sum(t);
+}
+
+// ---------------------------------------------------------------- math
+// tanh-approximate GELU exactly as ATen's CPU kernel evaluates it in fp32:
+// 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))  (reference modeling_gemma.py:134, modeling_siglip.py:162)
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float kBeta = 0.7978845608028654f;  // sqrt(2)*2/sqrt(pi)*0.5
+  const float kKappa = 0.044715f;
+  float inner = kBeta * (x + kKappa * (x * x * x));
+  return 0.5f * x * (1.f + tanhf(inner));
+}
+
+// Orderable 64-bit key for (value, index) argmax: larger value wins, ties go to the LOWER index
+// (torch.argmax returns the first maximal element).
+__device__ __forceinline__ unsigned long long argmax_key(float v, unsigned idx) {
+  unsigned b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+__device__ __forceinline__ unsigned argmax_key_index(unsigned long long k) {
+  return 0xffffffffu - (unsigned)(k & 0xffffffffull);
+}
+__device__ __forceinline__ float argmax_key_value(unsigned long long k) {
+  unsigned b = (unsigned)(k >> 32);
+  b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+  return __uint_as_float(b);
+}
+
+}  // namespace pg

@@ -1,0 +1,412 @@
+// Decode-path weight-streaming kernels (q_len == 1): every weight byte is read exactly once per
+// step with 128-bit loads, fp32 accumulation, and the reference's elementwise neighbours fused
+// in: RMSNorm prologue, RoPE + KV-append / GeGLU / residual / logits+argmax epilogues.
+// HBM-bound: bytes per step = the weight bytes.
+#include "common.cuh"
+
+namespace pg {
+
+constexpr int GEMV_THREADS = 256;
+constexpr int GEMV_WARPS = GEMV_THREADS / 32;
+
+// acc[r][b] += sum_k W[row r][k] * x[b][k] over this lane's share of K (K-range [k_begin,k_end)).
+// X_SMEM: x is fp32 in shared memory (normed prologue); else x is model-dtype global memory.
+template <typename T, int NB, int R, int U, bool X_SMEM>
+__device__ __forceinline__ void warp_dot(const T* const (&wrow)[R], const float* __restrict__ xs,
+                                         const T* __restrict__ xg, int K, int k_begin, int k_end,
+                                         float (&acc)[R][NB]) {
+  constexpr int V = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  for (int k0 = k_begin + lane * V; k0 < k_end; k0 += 32 * V * U) {
+    uint4 wv[U][R];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * 32 * V;
+#pragma unroll
+      for (int r = 0; r < R; ++r) wv[u][r] = (k < k_end) ? ldg_stream(wrow[r] + k) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * 32 * V;
+      if (k < k_end) {
+        float wf[R][V];
+#pragma unroll
+        for (int r = 0; r < R; ++r) unpack<T>(wv[u][r], wf[r]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          float xf[V];
+          if (X_SMEM) {
+#pragma unroll
+            for (int i = 0; i < V; i += 4) {
+              float4 t = *reinterpret_cast<const float4*>(xs + (size_t)b * K + k + i);
+              xf[i] = t.x; xf[i + 1] = t.y; xf[i + 2] = t.z; xf[i + 3] = t.w;
+            }
+          } else {
+            unpack<T>(ldg_cached(xg + (size_t)b * K + k), xf);
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[r][b] = fmaf(wf[r][i], xf[i], acc[r][b]);
+        }
+      }
+    }
+  }
+}
+
+// RMSNorm of NB rows into shared memory as fp32 values already rounded to the model dtype
+// (the reference materialises the normed tensor: modeling_gemma.py:120).
+template <typename T, int NB>
+__device__ __forceinline__ void norm_rows_to_smem(float* xs, const T* __restrict__ x, const T* __restrict__ w,
+                                                  int D, float eps) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float red[NB][GEMV_WARPS];
+  float ss[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+  for (int c = threadIdx.x * V; c < D; c += GEMV_THREADS * V) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float f[V];
+      unpack<T>(ldg_cached(x + (size_t)b * D + c), f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) ss[b] += f[i] * f[i];
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float v = warp_sum(ss[b]);
+    if (lane == 0) red[b][wid] = v;
+  }
+  __syncthreads();
+  float inv[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < GEMV_WARPS; ++i) t += red[b][i];
+    inv[b] = rsqrtf(t / (float)D + eps);
+  }
+  for (int c = threadIdx.x * V; c < D; c += GEMV_THREADS * V) {
+    float g[V];
+    unpack<T>(ldg_cached(w + c), g);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float f[V];
+      unpack<T>(ldg_cached(x + (size_t)b * D + c), f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) xs[(size_t)b * D + c + i] = rnd<T>((f[i] * inv[b]) * (1.0f + g[i]));
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ RMSNorm + QKV + RoPE + KV append
+template <typename T, int NB>
+__global__ void __launch_bounds__(GEMV_THREADS)
+decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __restrict__ norm_w,
+                  const T* __restrict__ W, const float* __restrict__ inv_freq,
+                  const int32_t* __restrict__ positions, T* __restrict__ k_pool, T* __restrict__ v_pool,
+                  const int32_t* __restrict__ page_table, int pt_stride, int page_size,
+                  const int32_t* __restrict__ kv_len, int D, int nq, int nkv, int hd, float eps, int max_pos) {
+  extern __shared__ __align__(16) float xs[];
+  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GEMV_WARPS;
+  const int half = hd / 2, units = (nq + 2 * nkv) * half;
+  for (int u = warp; u < units; u += nwarps) {
+    const int h = u / half, j = u % half;
+    const T* wrow[2] = {W + (size_t)(h * hd + j) * D, W + (size_t)(h * hd + j + half) * D};
+    float acc[2][NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[0][b] = acc[1][b] = 0.f;
+    warp_dot<T, NB, 2, 4, true>(wrow, xs, nullptr, D, 0, D, acc);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { acc[0][b] = warp_sum(acc[0][b]); acc[1][b] = warp_sum(acc[1][b]); }
+    if (lane < NB) {
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) if (b == lane) { a1 = acc[0][b]; a2 = acc[1][b]; }
+      const int b = lane;
+      const float x1 = rnd<T>(a1), x2 = rnd<T>(a2);
+      const int slot = kv_len[b];
+      const int page = page_table[(size_t)b * pt_stride + slot / page_size];
+      const size_t kv_row = ((size_t)page * page_size + (slot % page_size)) * (size_t)(nkv * hd);
+      if (h < nq + nkv) {
+        int pos = positions[b];
+        pos = min(max(pos, 0), max_pos - 1);
+        const float ang = (float)pos * inv_freq[j];
+        const float c = rnd<T>(cosf(ang)), s = rnd<T>(sinf(ang));
+        const float o1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(-x2 * s));
+        const float o2 = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
+        if (h < nq) {
+          T* qo = q_out + (size_t)b * nq * hd + h * hd;
+          qo[j] = from_f<T>(o1);
+          qo[j + half] = from_f<T>(o2);
+        } else {
+          T* ko = k_pool + kv_row + (h - nq) * hd;
+          ko[j] = from_f<T>(o1);
+          ko[j + half] = from_f<T>(o2);
+        }
+      } else {
+        T* vo = v_pool + kv_row + (h - nq - nkv) * hd;
+        vo[j] = from_f<T>(x1);
+        vo[j + half] = from_f<T>(x2);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ GEMV + residual (o_proj / down_proj)
+// KS warps share one output row (split along K, combined through shared memory).
+template <typename T, int NB, int KS>
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ W, const T* __restrict__ R,
+                int N, int K) {
+  constexpr int V = Vec<T>::N;
+  constexpr int ROWS_PER_CTA = GEMV_WARPS / KS;
+  __shared__ float part[GEMV_WARPS][NB];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rsub = wid / KS, ks = wid % KS;
+  // K-range of this warp, aligned to the vector width
+  const int seg = ((K / V + KS - 1) / KS) * V;
+  const int k_begin = ks * seg, k_end = min(K, k_begin + seg);
+  const int n_iter = (N + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+    const int n = it * ROWS_PER_CTA + rsub;
+    float acc[1][NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[0][b] = 0.f;
+    if (n < N) {
+      const T* wrow[1] = {W + (size_t)n * K};
+      warp_dot<T, NB, 1, 8, false>(wrow, nullptr, x, K, k_begin, k_end, acc);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[0][b] = warp_sum(acc[0][b]);
+    if (KS > 1) {
+      if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) part[wid][b] = acc[0][b];
+      }
+      __syncthreads();
+      if (ks == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          float t = 0.f;
+#pragma unroll
+          for (int i = 0; i < KS; ++i) t += part[rsub * KS + i][b];
+          acc[0][b] = t;
+        }
+      }
+    }
+    if (ks == 0 && n < N && lane < NB) {
+      float a = 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) if (b == lane) a = acc[0][b];
+      float v = rnd<T>(a);
+      if (R) v = rnd<T>(to_f<T>(R[(size_t)lane * N + n]) + v);
+      out[(size_t)lane * N + n] = from_f<T>(v);
+    }
+    if (KS > 1) __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ RMSNorm + gate/up + GeGLU
+template <typename T, int NB>
+__global__ void __launch_bounds__(GEMV_THREADS)
+decode_gateup_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ norm_w,
+                     const T* __restrict__ W, int D, int F, float eps) {
+  extern __shared__ __align__(16) float xs[];
+  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GEMV_WARPS;
+  for (int f = warp; f < F; f += nwarps) {
+    const T* wrow[2] = {W + (size_t)f * D, W + (size_t)(F + f) * D};
+    float acc[2][NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[0][b] = acc[1][b] = 0.f;
+    warp_dot<T, NB, 2, 4, true>(wrow, xs, nullptr, D, 0, D, acc);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { acc[0][b] = warp_sum(acc[0][b]); acc[1][b] = warp_sum(acc[1][b]); }
+    if (lane < NB) {
+      float g = 0.f, u = 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) if (b == lane) { g = acc[0][b]; u = acc[1][b]; }
+      const float act = rnd<T>(gelu_tanh(rnd<T>(g)));
+      out[(size_t)lane * F + f] = from_f<T>(act * rnd<T>(u));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ final RMSNorm + lm_head + argmax
+template <typename T, int NB>
+__global__ void __launch_bounds__(GEMV_THREADS)
+decode_lmhead_kernel(float* __restrict__ logits, const T* __restrict__ x, const T* __restrict__ norm_w,
+                     const T* __restrict__ W, int D, long long V, float eps, unsigned long long* keys) {
+  extern __shared__ __align__(16) float xs[];
+  __shared__ unsigned long long best_s[GEMV_WARPS][NB];
+  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long warp = (long long)blockIdx.x * GEMV_WARPS + wid, nwarps = (long long)gridDim.x * GEMV_WARPS;
+  const long long units = (V + 1) / 2;
+  unsigned long long best = 0ull;  // lane b < NB tracks batch row b
+  for (long long u = warp; u < units; u += nwarps) {
+    const long long r0 = 2 * u, r1 = (2 * u + 1 < V) ? 2 * u + 1 : 2 * u;
+    const T* wrow[2] = {W + (size_t)r0 * D, W + (size_t)r1 * D};
+    float acc[2][NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[0][b] = acc[1][b] = 0.f;
+    warp_dot<T, NB, 2, 4, true>(wrow, xs, nullptr, D, 0, D, acc);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { acc[0][b] = warp_sum(acc[0][b]); acc[1][b] = warp_sum(acc[1][b]); }
+    if (lane < NB) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) if (b == lane) { a0 = acc[0][b]; a1 = acc[1][b]; }
+      a0 = rnd<T>(a0); a1 = rnd<T>(a1);
+      float* lrow = logits + (size_t)lane * V;
+      lrow[r0] = a0;
+      unsigned long long k0 = argmax_key(a0, (unsigned)r0);
+      best = k0 > best ? k0 : best;
+      if (r1 != r0) {
+        lrow[r1] = a1;
+        unsigned long long k1 = argmax_key(a1, (unsigned)r1);
+        best = k1 > best ? k1 : best;
+      }
+    }
+  }
+  if (keys) {
+    if (lane < NB) best_s[wid][lane] = best;
+    __syncthreads();
+    if (wid == 0 && lane < NB) {
+      unsigned long long m = 0ull;
+#pragma unroll
+      for (int i = 0; i < GEMV_WARPS; ++i) m = best_s[i][lane] > m ? best_s[i][lane] : m;
+      if (m) atomicMax(&keys[lane], m);
+    }
+  }
+}
+
+template <typename F>
+static int dispatch_nb(int B, F&& f) {
+  switch (B) {
+    case 1: return f(std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>());
+    case 3: return f(std::integral_constant<int, 3>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 5: return f(std::integral_constant<int, 5>());
+    case 6: return f(std::integral_constant<int, 6>());
+    case 7: return f(std::integral_constant<int, 7>());
+    case 8: return f(std::integral_constant<int, 8>());
+  }
+  set_error("decode batch %d outside [1,%d]", B, PG_MAX_DECODE_BATCH);
+  return PG_ERR_INVALID;
+}
+
+static int grid_for_units(long long units, int per_cta) {
+  long long g = (units + per_cta - 1) / per_cta;
+  const long long cap = 148 * 2;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(%zu B smem) failed", bytes);
+      cudaGetLastError();
+      return PG_ERR_CUDA;
+    }
+  }
+  return PG_OK;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_qkv, const float* inv_freq,
+                  const int32_t* positions, void* k_pool, void* v_pool, const int32_t* page_table,
+                  int pt_stride, int page_size, const int32_t* kv_len, int B, int D, int nq, int nkv, int hd,
+                  float eps, int max_pos, int dtype, void* stream) {
+  PG_REQUIRE(hd % 2 == 0, "decode_qkv: odd head_dim");
+  const int units = (nq + 2 * nkv) * (hd / 2);
+  PG_DISPATCH_DTYPE(dtype, T, {
+    PG_REQUIRE(D % Vec<T>::N == 0, "decode_qkv: D=%d not vector aligned", D);
+    return dispatch_nb(B, [&](auto nb) {
+      constexpr int NB = decltype(nb)::value;
+      size_t smem = (size_t)NB * D * sizeof(float);
+      PG_REQUIRE(smem <= 200 * 1024, "decode_qkv: B*D too large for shared memory");
+      auto kern = decode_qkv_kernel<T, NB>;
+      if (int e = set_smem(kern, smem)) return e;
+      kern<<<grid_for_units(units, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
+          (T*)q_out, (const T*)x, (const T*)norm_w, (const T*)w_qkv, inv_freq, positions, (T*)k_pool,
+          (T*)v_pool, page_table, pt_stride, page_size, kv_len, D, nq, nkv, hd, eps, max_pos);
+      return check_launch("decode_qkv");
+    });
+  });
+  return PG_OK;
+}
+
+int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, int N, int K, int dtype,
+                void* stream) {
+  PG_DISPATCH_DTYPE(dtype, T, {
+    PG_REQUIRE(K % Vec<T>::N == 0, "gemv_res: K=%d not vector aligned", K);
+    return dispatch_nb(B, [&](auto nb) {
+      constexpr int NB = decltype(nb)::value;
+      if (K >= 8192) {
+        constexpr int KS = 4;
+        int iters = cdiv(N, GEMV_WARPS / KS);
+        gemv_res_kernel<T, NB, KS><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
+            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K);
+      } else {
+        int iters = cdiv(N, GEMV_WARPS);
+        gemv_res_kernel<T, NB, 1><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
+            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K);
+      }
+      return check_launch("gemv_res");
+    });
+  });
+  return PG_OK;
+}
+
+int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w_gu, int B, int D, int F,
+                     float eps, int dtype, void* stream) {
+  PG_DISPATCH_DTYPE(dtype, T, {
+    PG_REQUIRE(D % Vec<T>::N == 0, "decode_gateup: D=%d not vector aligned", D);
+    return dispatch_nb(B, [&](auto nb) {
+      constexpr int NB = decltype(nb)::value;
+      size_t smem = (size_t)NB * D * sizeof(float);
+      PG_REQUIRE(smem <= 200 * 1024, "decode_gateup: B*D too large for shared memory");
+      auto kern = decode_gateup_kernel<T, NB>;
+      if (int e = set_smem(kern, smem)) return e;
+      kern<<<grid_for_units(F, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
+          (T*)out, (const T*)x, (const T*)norm_w, (const T*)w_gu, D, F, eps);
+      return check_launch("decode_gateup");
+    });
+  });
+  return PG_OK;
+}
+
+int pg_decode_lmhead(float* logits, const void* x, const void* norm_w, const void* w_emb, int B, int D,
+                     int64_t V, float eps, unsigned long long* argmax_keys, int dtype, void* stream) {
+  PG_DISPATCH_DTYPE(dtype, T, {
+    PG_REQUIRE(D % Vec<T>::N == 0, "decode_lmhead: D=%d not vector aligned", D);
+    return dispatch_nb(B, [&](auto nb) {
+      constexpr int NB = decltype(nb)::value;
+      size_t smem = (size_t)NB * D * sizeof(float);
+      PG_REQUIRE(smem <= 200 * 1024, "decode_lmhead: B*D too large for shared memory");
+      auto kern = decode_lmhead_kernel<T, NB>;
+      if (int e = set_smem(kern, smem)) return e;
+      kern<<<grid_for_units((V + 1) / 2, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
+          logits, (const T*)x, (const T*)norm_w, (const T*)w_emb, D, (long long)V, eps, argmax_keys);
+      return check_launch("decode_lmhead");
+    });
+  });
+  return PG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+"""ctypes binding of libpg_b200.so (the C ABI declared in include/pg_b200.h).
+
+There is no fallback: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpg_b200.so")
+
+PG_F32, PG_BF16, PG_F16 = 0, 1, 2
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_RES, EPI_GEGLU = 0, 1, 2, 3, 4, 5
+MAX_DECODE_BATCH = 8
+
+DTYPE_CODE = {torch.float32: PG_F32, torch.bfloat16: PG_BF16, torch.float16: PG_F16}
+
+_vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
+
+# name -> argtypes (restype is int unless listed in _RESTYPE)
+SIGNATURES = {
+    "pg_last_error": [],
+    "pg_abi_version": [],
+    "pg_launch_count": [],
+    "pg_embed_merge": [_vp, _vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _i, _f, _f, _vp, _i, _vp],
+    "pg_rmsnorm": [_vp, _vp, _vp, _i, _i, _f, _i, _vp],
+    "pg_layernorm": [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp],
+    "pg_im2col": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "pg_gemm": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "pg_rope_append": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "pg_attention": [_vp, _i, _vp, _i, _vp, _vp, _i, _ll, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
+                     _f, _i, _i, _vp],
+    "pg_decode_qkv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f,
+                      _i, _i, _vp],
+    "pg_decode_attention_ws_floats": [_i, _i, _i, _i],
+    "pg_decode_attention": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _i,
+                            _i, _vp],
+    "pg_gemv_res": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "pg_decode_gateup": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
+    "pg_decode_lmhead": [_vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _i, _vp],
+    "pg_step_advance": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "pg_argmax": [_vp, _vp, _vp, _i, _ll, _vp],
+    "pg_top_p_sample": [_vp, _vp, _vp, _i, _ll, _f, _f, _ull, _vp, _vp, _vp],
+    "pg_kv_gather": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+}
+_RESTYPE = {"pg_last_error": C.c_char_p, "pg_launch_count": _ull, "pg_decode_attention_ws_floats": _ll}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C .../csrc`).  pg_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPE.get(name, C.c_int)
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return (lib().pg_last_error() or b"").decode()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RuntimeError(f"pg_b200 {what} failed (code {rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().pg_launch_count())

@@ -1,0 +1,489 @@
+"""Host side of the B200 PaliGemma engine: weight repack, paged KV pool, and the launch
+sequences (vision tower, prefill / cache-off recompute, decode step, CUDA-graph decode loop).
+
+PyTorch is used for device memory, streams and CUDA-graph capture only; every FLOP of the
+hot path runs in libpg_b200.so through the C ABI of include/pg_b200.h.  There is no CPU or
+PyTorch-op fallback: a missing library or a non-CUDA tensor raises.
+
+Reference semantics reproduced: attention is never masked (Q1);
+prefill positions 0..N-1 (Q2); cached steps use position = attention-mask length, i.e.
+N+t, skipping N (Q3); a q_len>1 forward on a non-empty cache gives every new token that
+same position (Q6, patched merge); pad ids embed to zero rows (Q8); the sqrt(D)
+normaliser is rounded to the model dtype while image features are divided by the exact
+float (Q9); RoPE inv_freq is rounded to the model dtype by `model.to(dtype)`.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Mapping, Optional
+
+import torch
+
+from . import _cabi as cabi
+from ._cabi import ptr
+
+
+def _get(obj, name, default=None):
+    if isinstance(obj, Mapping):
+        return obj.get(name, default)
+    return getattr(obj, name, default)
+
+
+@dataclass
+class Dims:
+    # text
+    V: int; D: int; F: int; L: int; nq: int; nkv: int; hd: int; eps: float; theta: float; max_pos: int
+    # vision
+    Hv: int; Iv: int; Lv: int; heads_v: int; C: int; S: int; p: int; eps_v: float
+    # glue
+    image_token_index: int; pad_token_id: int; hidden_size: int
+
+    @property
+    def P(self) -> int:
+        return (self.S // self.p) ** 2
+
+    @staticmethod
+    def from_config(cfg) -> "Dims":
+        v, t = _get(cfg, "vision_config"), _get(cfg, "text_config")
+        pad = _get(cfg, "pad_token_id")
+        return Dims(
+            V=_get(t, "vocab_size"), D=_get(t, "hidden_size"), F=_get(t, "intermediate_size"),
+            L=_get(t, "num_hidden_layers"), nq=_get(t, "num_attention_heads"),
+            nkv=_get(t, "num_key_value_heads"), hd=_get(t, "head_dim", 256),
+            eps=_get(t, "rms_norm_eps", 1e-6), theta=_get(t, "rope_theta", 10000.0),
+            max_pos=_get(t, "max_position_embeddings", 8192),
+            Hv=_get(v, "hidden_size"), Iv=_get(v, "intermediate_size"), Lv=_get(v, "num_hidden_layers"),
+            heads_v=_get(v, "num_attention_heads"), C=_get(v, "num_channels", 3), S=_get(v, "image_size"),
+            p=_get(v, "patch_size"), eps_v=_get(v, "layer_norm_eps", 1e-6),
+            image_token_index=_get(cfg, "image_token_index"), pad_token_id=-1 if pad is None else pad,
+            hidden_size=_get(cfg, "hidden_size"))
+
+
+class PagedKV:
+    """Device state of one batch of sequences in the paged KV pool (the storage behind the
+    reference's KVCache, modeling_gemma.py:10-36)."""
+
+    def __init__(self, engine: "PaliGemmaEngine", batch: int):
+        self.engine = engine
+        self.batch = batch
+        self.length = 0                      # entries per sequence (host mirror)
+        self.pages: List[List[int]] = [[] for _ in range(batch)]
+        self.max_pages = 0
+        self.page_table: Optional[torch.Tensor] = None   # int32 [batch, max_pages] device
+        self.kv_len = torch.zeros(batch, dtype=torch.int32, device=engine.device)
+
+    def reserve(self, total_len: int) -> None:
+        """Make sure every sequence owns pages for `total_len` entries."""
+        eng = self.engine
+        need = (total_len + eng.page_size - 1) // eng.page_size
+        if need <= len(self.pages[0]):
+            return
+        grow = max(need, min(2 * len(self.pages[0]), need + 8))
+        for b in range(self.batch):
+            self.pages[b].extend(eng._alloc_pages(grow - len(self.pages[b])))
+        self.max_pages = grow
+        self.page_table = torch.tensor(self.pages, dtype=torch.int32, device=eng.device)
+
+    def release(self) -> None:
+        if self.engine is not None:
+            for p in self.pages:
+                self.engine._free_pages(p)
+        self.pages = [[] for _ in range(self.batch)]
+        self.length = 0
+        self.page_table = None
+        self.max_pages = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def gather(self, layer: int, which: str) -> torch.Tensor:
+        """Contiguous (B, n_kv, T, hd) copy of one layer's keys or values."""
+        eng, d = self.engine, self.engine.dims
+        out = torch.empty((self.batch, d.nkv, self.length, d.hd), dtype=eng.dtype, device=eng.device)
+        if self.length:
+            pool = eng.k_pool[layer] if which == "k" else eng.v_pool[layer]
+            cabi.check(cabi.lib().pg_kv_gather(ptr(out), ptr(pool), ptr(self.page_table), self.max_pages,
+                                               eng.page_size, self.batch, self.length, d.nkv, d.hd,
+                                               eng.dt, cabi.stream()), "kv_gather")
+        return out
+
+
+class PaliGemmaEngine:
+    """Owns repacked weights + the KV pool and issues the kernel sequences."""
+
+    def __init__(self, config, weights: Mapping[str, torch.Tensor], *, device=None, dtype=None,
+                 page_size: int = 64, kv_pool_tokens: int = 65536, gemm_impl: int = 0,
+                 adopt=None):
+        cabi.lib()  # fail now if the CUDA library is missing
+        self.dims = d = Dims.from_config(config)
+        emb = weights["language_model.model.embed_tokens.weight"]
+        self.device = torch.device(device) if device is not None else emb.device
+        if self.device.type != "cuda":
+            raise RuntimeError("pg_b200 runs on CUDA devices only (no CPU fallback); move the model to 'cuda'")
+        self.dtype = dtype or emb.dtype
+        if self.dtype not in cabi.DTYPE_CODE:
+            raise RuntimeError(f"unsupported model dtype {self.dtype}")
+        self.dt = cabi.DTYPE_CODE[self.dtype]
+        self.gemm_impl = gemm_impl
+        self.page_size = page_size
+        self._vec = 4 if self.dtype == torch.float32 else 8
+        self._repack(weights, adopt)
+        # paged KV pool: [L, pages, page_size, nkv*hd] for K and for V
+        self.num_pages = max(8, (kv_pool_tokens + page_size - 1) // page_size)
+        self.k_pool = torch.zeros((d.L, self.num_pages, page_size, d.nkv * d.hd), dtype=self.dtype, device=self.device)
+        self.v_pool = torch.zeros_like(self.k_pool)
+        self._free = list(range(self.num_pages - 1, -1, -1))
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.max_splits = 32
+        self._decode_states: Dict[tuple, "DecodeState"] = {}
+
+    # ------------------------------------------------------------------ weights
+    def _w(self, weights, key):
+        t = weights[key]
+        if t.device != self.device or t.dtype != self.dtype:
+            t = t.to(device=self.device, dtype=self.dtype)
+        return t.contiguous()
+
+    def _repack(self, weights, adopt):
+        """Fuse q/k/v and gate/up, pad the patch-embed K, keep HF layout otherwise.
+        `adopt(key, view)` lets the nn.Module owner re-point its parameters at the fused
+        storage so the checkpoint is not held twice."""
+        d = self.dims
+        W = lambda k: self._w(weights, k)
+        vm = "vision_tower.vision_model."
+        kc = d.C * d.p * d.p
+        self.k_patch = ((kc + self._vec - 1) // self._vec) * self._vec
+        wp = torch.zeros((d.Hv, self.k_patch), dtype=self.dtype, device=self.device)
+        wp[:, :kc] = W(vm + "embeddings.patch_embedding.weight").reshape(d.Hv, kc)
+        self.v_patch_w, self.v_patch_b = wp, W(vm + "embeddings.patch_embedding.bias")
+        self.v_pos = W(vm + "embeddings.position_embedding.weight")
+        self.v_layers = []
+        for i in range(d.Lv):
+            Lk = f"{vm}encoder.layers.{i}."
+            qkv_w = torch.cat([W(Lk + f"self_attn.{n}.weight") for n in ("q_proj", "k_proj", "v_proj")], 0)
+            qkv_b = torch.cat([W(Lk + f"self_attn.{n}.bias") for n in ("q_proj", "k_proj", "v_proj")], 0)
+            if adopt:
+                for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+                    adopt(Lk + f"self_attn.{n}.weight", qkv_w[j * d.Hv:(j + 1) * d.Hv])
+            self.v_layers.append(dict(
+                ln1_w=W(Lk + "layer_norm1.weight"), ln1_b=W(Lk + "layer_norm1.bias"),
+                qkv_w=qkv_w, qkv_b=qkv_b,
+                o_w=W(Lk + "self_attn.out_proj.weight"), o_b=W(Lk + "self_attn.out_proj.bias"),
+                ln2_w=W(Lk + "layer_norm2.weight"), ln2_b=W(Lk + "layer_norm2.bias"),
+                fc1_w=W(Lk + "mlp.fc1.weight"), fc1_b=W(Lk + "mlp.fc1.bias"),
+                fc2_w=W(Lk + "mlp.fc2.weight"), fc2_b=W(Lk + "mlp.fc2.bias")))
+        self.v_post_w, self.v_post_b = W(vm + "post_layernorm.weight"), W(vm + "post_layernorm.bias")
+        self.proj_w, self.proj_b = W("multi_modal_projector.linear.weight"), W("multi_modal_projector.linear.bias")
+        lm = "language_model.model."
+        self.emb = W(lm + "embed_tokens.weight")
+        head = weights.get("language_model.lm_head.weight")
+        self.lm_head = self.emb if (head is None or head.data_ptr() == weights[lm + "embed_tokens.weight"].data_ptr()) \
+            else W("language_model.lm_head.weight")
+        self.t_layers = []
+        for i in range(d.L):
+            Lk = f"{lm}layers.{i}."
+            names = ("q_proj", "k_proj", "v_proj")
+            qkv = torch.cat([W(Lk + f"self_attn.{n}.weight") for n in names], 0)
+            gu = torch.cat([W(Lk + "mlp.gate_proj.weight"), W(Lk + "mlp.up_proj.weight")], 0)
+            if adopt:
+                off = 0
+                for n in names:
+                    rows = weights[Lk + f"self_attn.{n}.weight"].shape[0]
+                    adopt(Lk + f"self_attn.{n}.weight", qkv[off:off + rows])
+                    off += rows
+                adopt(Lk + "mlp.gate_proj.weight", gu[:d.F])
+                adopt(Lk + "mlp.up_proj.weight", gu[d.F:])
+            self.t_layers.append(dict(
+                ln1=W(Lk + "input_layernorm.weight"), qkv=qkv, o=W(Lk + "self_attn.o_proj.weight"),
+                ln2=W(Lk + "post_attention_layernorm.weight"), gu=gu, down=W(Lk + "mlp.down_proj.weight")))
+        self.final_norm = W(lm + "norm.weight")
+        # RoPE frequencies (modeling_gemma.py:151): the buffer is rounded by model.to(dtype)
+        f = 1.0 / (d.theta ** (torch.arange(0, d.hd, 2, dtype=torch.int64).float() / d.hd))
+        self.inv_freq = f.to(self.dtype).float().to(self.device)
+        # sqrt(D) normaliser rounded to the model dtype (:367); image divisor is the exact float (:481)
+        self.normalizer = float(torch.tensor(d.D ** 0.5, dtype=self.dtype).float())
+        self.img_div = float(torch.tensor(d.hidden_size ** 0.5, dtype=torch.float32))
+
+    def weight_bytes_per_decode_step(self) -> int:
+        """Algorithmic HBM bytes one decode step must read from the weights."""
+        d, e = self.dims, torch.tensor([], dtype=self.dtype).element_size()
+        per_layer = ((d.nq + 2 * d.nkv) * d.hd * d.D + d.D * d.nq * d.hd + 3 * d.F * d.D + 2 * d.D)
+        return e * (d.L * per_layer + d.V * d.D + d.D)
+
+    # ------------------------------------------------------------------ KV pages
+    def _alloc_pages(self, n: int) -> List[int]:
+        if n > len(self._free):
+            raise RuntimeError(f"KV pool exhausted: need {n} pages, {len(self._free)} free "
+                               f"(pool holds {self.num_pages * self.page_size} tokens; raise kv_pool_tokens)")
+        out = [self._free.pop() for _ in range(n)]
+        return out
+
+    def _free_pages(self, pages: List[int]) -> None:
+        self._free.extend(reversed(pages))
+
+    def new_kv(self, batch: int) -> PagedKV:
+        return PagedKV(self, batch)
+
+    # ------------------------------------------------------------------ op wrappers
+    def _gemm(self, out, a, w, bias=None, res=None, epi=cabi.EPI_NONE, res_mod=0, out_f32=False,
+              M=None, N=None, K=None, lda=None, ldc=None):
+        M = a.shape[0] if M is None else M
+        K = a.shape[1] if K is None else K
+        if N is None:
+            N = w.shape[0] // 2 if epi == cabi.EPI_GEGLU else w.shape[0]
+        lda = a.stride(0) if lda is None else lda
+        ldc = out.stride(0) if ldc is None else ldc
+        cabi.check(cabi.lib().pg_gemm(ptr(out), ptr(a), ptr(w), ptr(bias), ptr(res), M, N, K, lda,
+                                      w.stride(0), ldc, 0 if res is None else res.stride(0), res_mod, epi,
+                                      1 if out_f32 else 0, self.gemm_impl, self.dt, cabi.stream()), "gemm")
+        return out
+
+    def _new(self, *shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.dtype, device=self.device)
+
+    # ------------------------------------------------------------------ vision tower + projector
+    def vision_features(self, pixels: torch.Tensor) -> torch.Tensor:
+        """SiglipVisionModel.forward (modeling_siglip.py:236-255): (B,C,S,S) -> (B,P,Hv)."""
+        d, L = self.dims, cabi.lib()
+        if pixels.device != self.device:
+            raise RuntimeError("pixel_values must live on the model's CUDA device")
+        px = pixels.to(self.dtype).contiguous()
+        B, T = px.shape[0], px.shape[0] * d.P
+        st = cabi.stream()
+        col = self._new(T, self.k_patch)
+        cabi.check(L.pg_im2col(ptr(col), ptr(px), B, d.C, d.S, d.S, d.p, self.k_patch, self.dt, st), "im2col")
+        h = self._new(T, d.Hv)
+        self._gemm(h, col, self.v_patch_w, self.v_patch_b, self.v_pos, cabi.EPI_BIAS_RES, res_mod=d.P)
+        ln, qkv, att = self._new(T, d.Hv), self._new(T, 3 * d.Hv), self._new(T, d.Hv)
+        h2, mid = self._new(T, d.Hv), self._new(T, d.Iv)
+        hdv = d.Hv // d.heads_v
+        scale = float(hdv ** -0.5)
+        for w in self.v_layers:
+            cabi.check(L.pg_layernorm(ptr(ln), ptr(h), ptr(w["ln1_w"]), ptr(w["ln1_b"]), T, d.Hv, d.eps_v, self.dt, st), "ln1")
+            self._gemm(qkv, ln, w["qkv_w"], w["qkv_b"], None, cabi.EPI_BIAS)
+            cabi.check(L.pg_attention(ptr(att), d.Hv, ptr(qkv), 3 * d.Hv, qkv[:, d.Hv:].data_ptr(),
+                                      qkv[:, 2 * d.Hv:].data_ptr(), 3 * d.Hv, d.P * 3 * d.Hv, None, 0, 0,
+                                      None, d.P, 0, B, d.P, d.heads_v, d.heads_v, hdv, scale, 0, self.dt, st),
+                       "siglip attention")
+            self._gemm(h2, att, w["o_w"], w["o_b"], h, cabi.EPI_BIAS_RES)
+            cabi.check(L.pg_layernorm(ptr(ln), ptr(h2), ptr(w["ln2_w"]), ptr(w["ln2_b"]), T, d.Hv, d.eps_v, self.dt, st), "ln2")
+            self._gemm(mid, ln, w["fc1_w"], w["fc1_b"], None, cabi.EPI_BIAS_GELU)
+            self._gemm(h, mid, w["fc2_w"], w["fc2_b"], h2, cabi.EPI_BIAS_RES)
+        out = self._new(T, d.Hv)
+        cabi.check(L.pg_layernorm(ptr(out), ptr(h), ptr(self.v_post_w), ptr(self.v_post_b), T, d.Hv, d.eps_v, self.dt, st), "post_ln")
+        return out.view(B, d.P, d.Hv)
+
+    def project(self, feats: torch.Tensor) -> torch.Tensor:
+        """PaliGemmaMultiModalProjector.forward (modeling_gemma.py:435-438)."""
+        d = self.dims
+        x = feats.reshape(-1, d.Hv)
+        out = self._new(x.shape[0], self.proj_w.shape[0])
+        self._gemm(out, x, self.proj_w, self.proj_b, None, cabi.EPI_BIAS)
+        return out.view(*feats.shape[:-1], self.proj_w.shape[0])
+
+    def encode_images(self, pixels: torch.Tensor) -> torch.Tensor:
+        return self.project(self.vision_features(pixels))
+
+    # ------------------------------------------------------------------ text: q_len >= 1, general
+    def text_forward(self, input_ids: torch.Tensor, image_features: Optional[torch.Tensor],
+                     kv: Optional[PagedKV], position_value: Optional[int] = None,
+                     logits: str = "all") -> torch.Tensor:
+        """Embed+merge, L decoder layers, final norm, lm_head for a (B,q) block of new tokens.
+
+        kv=None reproduces `kv_cache=None` (nothing persists).  With an empty cache the new
+        tokens get positions 0..q-1; with a non-empty cache every new token gets
+        `position_value` (the attention-mask length).  Returns fp32 logits (B,q,V) or, with
+        logits='last', (B,1,V)."""
+        d, L, st = self.dims, cabi.lib(), cabi.stream()
+        B, q = input_ids.shape
+        T = B * q
+        ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        temp = kv is None
+        if temp:
+            kv = self.new_kv(B)
+        try:
+            if kv.batch != B:
+                raise ValueError(f"kv cache holds batch {kv.batch}, input has batch {B}")
+            cached = kv.length
+            kv.reserve(cached + q)
+            if cached == 0:
+                pos = torch.arange(q, dtype=torch.int32, device=self.device).repeat(B)
+            else:
+                pos = torch.full((T,), int(position_value), dtype=torch.int32, device=self.device)
+            img = None if image_features is None or image_features.numel() == 0 else \
+                image_features.reshape(-1, d.D).to(self.dtype).contiguous()
+            x = self._new(T, d.D)
+            self.err_flag.zero_()
+            cabi.check(L.pg_embed_merge(ptr(x), ptr(ids), ptr(self.emb), ptr(img), T, d.D, d.V,
+                                        d.image_token_index, d.pad_token_id, 0 if img is None else img.shape[0],
+                                        self.img_div, self.normalizer, ptr(self.err_flag), self.dt, st), "embed_merge")
+            nqkv = (d.nq + 2 * d.nkv) * d.hd
+            n, qkv, qo = self._new(T, d.D), self._new(T, nqkv), self._new(T, d.nq * d.hd)
+            att, x2, g = self._new(T, d.nq * d.hd), self._new(T, d.D), self._new(T, d.F)
+            scale_div = float(math.sqrt(d.hd))
+            for li, w in enumerate(self.t_layers):
+                cabi.check(L.pg_rmsnorm(ptr(n), ptr(x), ptr(w["ln1"]), T, d.D, d.eps, self.dt, st), "rmsnorm")
+                self._gemm(qkv, n, w["qkv"])
+                cabi.check(L.pg_rope_append(ptr(qo), ptr(qkv), ptr(self.inv_freq), ptr(pos), ptr(self.k_pool[li]),
+                                            ptr(self.v_pool[li]), ptr(kv.page_table), kv.max_pages, self.page_size,
+                                            ptr(kv.kv_len), B, q, d.nq, d.nkv, d.hd, d.max_pos, self.dt, st), "rope_append")
+                cabi.check(L.pg_attention(ptr(att), d.nq * d.hd, ptr(qo), d.nq * d.hd, ptr(self.k_pool[li]),
+                                          ptr(self.v_pool[li]), 0, 0, ptr(kv.page_table), kv.max_pages, self.page_size,
+                                          ptr(kv.kv_len), 0, q, B, q, d.nq, d.nkv, d.hd, scale_div, 1, self.dt, st),
+                           "attention")
+                self._gemm(x2, att, w["o"], None, x, cabi.EPI_RES)
+                cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), T, d.D, d.eps, self.dt, st), "rmsnorm")
+                self._gemm(g, n, w["gu"], None, None, cabi.EPI_GEGLU)
+                self._gemm(x, g, w["down"], None, x2, cabi.EPI_RES)
+            kv.kv_len.add_(q)
+            kv.length = cached + q
+            if logits == "last":
+                x = x.view(B, q, d.D)[:, -1].contiguous()
+            rows = x.shape[0]
+            h = self._new(rows, d.D)
+            cabi.check(L.pg_rmsnorm(ptr(h), ptr(x), ptr(self.final_norm), rows, d.D, d.eps, self.dt, st), "final norm")
+            out = self._new(rows, d.V, dtype=torch.float32)
+            self._gemm(out, h, self.lm_head, out_f32=True)
+            return out.view(B, -1, d.V)
+        finally:
+            if temp:
+                kv.release()
+
+    def check_errors(self) -> None:
+        """Raise if a kernel flagged an id problem (image token without image rows, id out of range):
+        the reference raises from masked_scatter / embedding for the same inputs."""
+        if int(self.err_flag.item()) != 0:
+            self.err_flag.zero_()
+            raise RuntimeError("input_ids held an image token with no image feature left, or an id outside the vocabulary")
+
+    # ------------------------------------------------------------------ decode (q_len == 1)
+    def decode_state(self, batch: int) -> "DecodeState":
+        key = (batch,)
+        if key not in self._decode_states:
+            self._decode_states[key] = DecodeState(self, batch)
+        return self._decode_states[key]
+
+
+class DecodeState:
+    """Static device buffers + CUDA graph of one decode step for a fixed batch size.
+
+    Everything a step needs that changes between steps (token ids, positions, KV lengths, page
+    table, RNG offset) lives in device memory the graph re-reads, so one captured graph serves the
+    whole generation and the host never has to synchronise per token."""
+
+    def __init__(self, eng: PaliGemmaEngine, batch: int):
+        self.eng, self.B = eng, batch
+        d, dev = eng.dims, eng.device
+        self.ids = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.keys = torch.zeros(batch, dtype=torch.int64, device=dev)  # u64 argmax keys
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.max_hist = 4096
+        self.history = torch.zeros((batch, self.max_hist), dtype=torch.int64, device=dev)
+        self.logits = torch.zeros((batch, d.V), dtype=torch.float32, device=dev)
+        self.probs = None
+        self.sampled = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.x = eng._new(batch, d.D)
+        self.x2 = eng._new(batch, d.D)
+        self.q = eng._new(batch, d.nq * d.hd)
+        self.att = eng._new(batch, d.nq * d.hd)
+        self.g = eng._new(batch, d.F)
+        nws = cabi.lib().pg_decode_attention_ws_floats(batch, d.nq, d.hd, eng.max_splits)
+        self.ws = torch.zeros(int(nws), dtype=torch.float32, device=dev)
+        self.counters = torch.zeros(batch * d.nkv, dtype=torch.int32, device=dev)
+        self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.kv: Optional[PagedKV] = None
+        self.kv_table_ptr = None
+
+    # one decode step: kernels only, no host sync, capturable
+    def launch_step(self, kv: PagedKV, sample: Optional[tuple] = None, advance: bool = True) -> None:
+        eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
+        B, dt = self.B, self.eng.dt
+        cabi.check(L.pg_embed_merge(ptr(self.x), ptr(self.ids), ptr(eng.emb), None, B, d.D, d.V,
+                                    d.image_token_index, d.pad_token_id, 0, eng.img_div, eng.normalizer,
+                                    ptr(eng.err_flag), dt, st), "embed")
+        scale_div = float(math.sqrt(d.hd))
+        MB = cabi.MAX_DECODE_BATCH
+        x, x2 = self.x, self.x2
+        for li, w in enumerate(eng.t_layers):
+            kp, vp = eng.k_pool[li], eng.v_pool[li]
+            for b0 in range(0, B, MB):
+                nb = min(MB, B - b0)
+                cabi.check(L.pg_decode_qkv(ptr(self.q[b0:]), ptr(x[b0:]), ptr(w["ln1"]), ptr(w["qkv"]), ptr(eng.inv_freq),
+                                           ptr(self.pos[b0:]), ptr(kp), ptr(vp), ptr(kv.page_table[b0:]), kv.max_pages,
+                                           eng.page_size, ptr(kv.kv_len[b0:]), nb, d.D, d.nq, d.nkv, d.hd, d.eps,
+                                           d.max_pos, dt, st), "decode_qkv")
+            cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
+                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, d.nq, d.nkv, d.hd,
+                                             scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
+                       "decode_attention")
+            for b0 in range(0, B, MB):
+                nb = min(MB, B - b0)
+                cabi.check(L.pg_gemv_res(ptr(x2[b0:]), ptr(self.att[b0:]), ptr(w["o"]), ptr(x[b0:]), nb, d.D,
+                                         d.nq * d.hd, dt, st), "o_proj")
+                cabi.check(L.pg_decode_gateup(ptr(self.g[b0:]), ptr(x2[b0:]), ptr(w["ln2"]), ptr(w["gu"]), nb, d.D,
+                                              d.F, d.eps, dt, st), "gateup")
+                cabi.check(L.pg_gemv_res(ptr(x[b0:]), ptr(self.g[b0:]), ptr(w["down"]), ptr(x2[b0:]), nb, d.D, d.F,
+                                         dt, st), "down_proj")
+        for b0 in range(0, B, MB):
+            nb = min(MB, B - b0)
+            cabi.check(L.pg_decode_lmhead(ptr(self.logits[b0:]), ptr(x[b0:]), ptr(eng.final_norm), ptr(eng.lm_head),
+                                          nb, d.D, d.V, d.eps, ptr(self.keys[b0:]), dt, st), "lm_head")
+        sampled = None
+        if sample is not None:
+            temperature, top_p, seed = sample
+            if self.probs is None:
+                self.probs = torch.empty_like(self.logits)
+            cabi.check(L.pg_top_p_sample(ptr(self.sampled), ptr(self.logits), ptr(self.probs), B, d.V,
+                                         float(temperature), float(top_p), int(seed), ptr(self.step), None, st),
+                       "top_p")
+            sampled = self.sampled
+        if advance:
+            cabi.check(L.pg_step_advance(ptr(self.ids), ptr(self.history), self.max_hist, ptr(self.step),
+                                         ptr(self.keys), ptr(sampled), ptr(kv.kv_len), ptr(self.pos), B, st),
+                       "step_advance")
+
+    def bind(self, kv: PagedKV, next_ids: torch.Tensor, position: int) -> None:
+        """Point the step at a cache and seed ids / positions (host -> device, outside the graph)."""
+        self.kv = kv
+        self.ids.copy_(next_ids.reshape(-1).to(torch.int64))
+        self.pos.fill_(int(position))
+        self.step.zero_()
+        self.keys.zero_()
+
+    def run_steps(self, kv: PagedKV, n_steps: int, sample: Optional[tuple] = None, use_graph: bool = True) -> None:
+        """Advance n_steps tokens entirely on the device (tokens land in self.history)."""
+        if n_steps > self.max_hist:
+            raise ValueError("too many steps for the history buffer")
+        kv.reserve(kv.length + n_steps)
+        if not use_graph:
+            for _ in range(n_steps):
+                self.launch_step(kv, sample)
+        else:
+            key = (kv.page_table.data_ptr(), kv.kv_len.data_ptr(), kv.max_pages, sample)
+            g = self.graphs.get(key)
+            if g is None:
+                # warm up on a side stream (lazy module loading, smem attributes), undo its effects
+                saved = [t.clone() for t in (self.ids, self.pos, self.step, self.keys, kv.kv_len, self.history[:, :1])]
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self.launch_step(kv, sample)
+                torch.cuda.current_stream().wait_stream(s)
+                for t, v in zip((self.ids, self.pos, self.step, self.keys, kv.kv_len, self.history[:, :1]), saved):
+                    t.copy_(v)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.launch_step(kv, sample)
+                for t, v in zip((self.ids, self.pos, self.step, self.keys, kv.kv_len, self.history[:, :1]), saved):
+                    t.copy_(v)
+                if len(self.graphs) > 8:
+                    self.graphs.clear()
+                self.graphs[key] = g
+            for _ in range(n_steps):
+                g.replay()
+        kv.length += n_steps

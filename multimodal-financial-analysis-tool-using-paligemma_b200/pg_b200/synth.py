@@ -217,3 +217,67 @@ def synth_prompt_ids(cfg: dict, batch: int = 1, prefix_len: int | None = None,
             body = torch.randint(3, img, (prefix_len - 2,), generator=g).tolist()
         rows.append([img] * nimg + [BOS_ID] + body + [NEWLINE_ID])
     return torch.tensor(rows, dtype=torch.int64)
+
+
+class StubTokenizer:
+    """Offline stand-in for the HF Gemma tokenizer (no tokenizer.model on disk): whitespace-free
+    greedy matching of the special strings the processor emits, hashed ids for everything else.
+    Implements exactly the surface PaliGemmaProcessor touches (reference
+    processing_paligemma.py:63-75,108-113) plus decode() for the generation loop."""
+
+    def __init__(self, vocab_size: int = 257216, image_token_id: int = 257152):
+        self.vocab_size, self._image_id = vocab_size, image_token_id
+        self.bos_token, self.eos_token = "<bos>", "<eos>"
+        self.bos_token_id, self.eos_token_id, self.pad_token_id = BOS_ID, EOS_ID, PAD_ID
+        self.add_bos_token = self.add_eos_token = True
+        self._special = {"<bos>": BOS_ID, "<eos>": EOS_ID, "<pad>": PAD_ID, "\n": NEWLINE_ID}
+        self.added_tokens = []
+
+    def add_special_tokens(self, mapping):
+        for tok in mapping.get("additional_special_tokens", []):
+            self._special[tok] = self._image_id if tok == "<image>" else self._hash(tok)
+        return len(mapping.get("additional_special_tokens", []))
+
+    def add_tokens(self, tokens):
+        self.added_tokens.extend(tokens)
+        return len(tokens)
+
+    def convert_tokens_to_ids(self, tok):
+        return self._special.get(tok, self._hash(tok))
+
+    def _hash(self, word: str) -> int:
+        return 3 + zlib.crc32(word.encode()) % (min(self._image_id, self.vocab_size) - 3)
+
+    def _encode(self, text: str):
+        ids, i = [], 0
+        specials = sorted(self._special, key=len, reverse=True)
+        word = ""
+        while i < len(text):
+            for s in specials:
+                if text.startswith(s, i):
+                    if word:
+                        ids.append(self._hash(word)); word = ""
+                    ids.append(self._special[s]); i += len(s)
+                    break
+            else:
+                if text[i] == " ":
+                    if word:
+                        ids.append(self._hash(word)); word = ""
+                else:
+                    word += text[i]
+                i += 1
+        if word:
+            ids.append(self._hash(word))
+        return ids
+
+    def __call__(self, texts, return_tensors="pt", padding="longest", truncation=True):
+        rows = [self._encode(t) for t in texts]
+        n = max(len(r) for r in rows)
+        ids = torch.tensor([r + [PAD_ID] * (n - len(r)) for r in rows], dtype=torch.int64)
+        mask = torch.tensor([[1] * len(r) + [0] * (n - len(r)) for r in rows], dtype=torch.int64)
+        return {"input_ids": ids, "attention_mask": mask}
+
+    def decode(self, ids, skip_special_tokens=True):
+        ids = ids.tolist() if hasattr(ids, "tolist") else list(ids)
+        drop = set(self._special.values()) if skip_special_tokens else set()
+        return " ".join(f"<{i}>" for i in ids if i not in drop)
