@@ -97,6 +97,13 @@ int pg_attention(void* out, int ld_out, const void* q, int ld_q, const void* k, 
 /* ---- decode path (q_len == 1 per sequence), B <= PG_MAX_DECODE_BATCH per call ----------- */
 #define PG_MAX_DECODE_BATCH 8
 
+/* L2 prefetch chain: registers [ptr, ptr+bytes) (16-byte aligned; normally the NEXT kernel's
+ * weights) with the calling thread; the next pg_decode_* / pg_gemv_res launch from this thread
+ * consumes it and starts by issuing cp.async.bulk.prefetch.L2 for that region, one slice per CTA.
+ * Weights never depend on activations, so HBM keeps streaming through the small latency-bound
+ * kernels and across kernel boundaries.  Purely a performance hint: results never change. */
+int pg_set_next_prefetch(const void* ptr, long long bytes);
+
 /* input RMSNorm + fused q/k/v projection + RoPE + KV append (GemmaDecoderLayer.forward
  * :314-316, GemmaAttention.forward :241-259).  x: [B,D] residual stream. positions/kv_len:
  * device int32[B]; K,V go to slot kv_len[b]. */

@@ -58,11 +58,35 @@ template <> struct Vec<bf16> { static constexpr int N = 8; };
 template <> struct Vec<f16> { static constexpr int N = 8; };
 
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
-  // weights are read exactly once per step: bypass L1 allocation
+  // weights are read exactly once per step: no L1 allocation, first to leave L2 (so they do not
+  // push out the lines the prefetch chain staged for the next kernels)
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
   return r;
+}
+
+// ---------------------------------------------------------------- L2 prefetch chain
+// Every decode kernel starts by asking the L2 for its CTA's share of the NEXT kernel's weights
+// (cp.async.bulk.prefetch.L2): the weights never depend on activations, so HBM keeps streaming
+// through the small latency-bound kernels and across kernel boundaries.
+struct Prefetch { const char* ptr; unsigned long long bytes; };
+Prefetch take_prefetch();  // host side: the region registered by pg_set_next_prefetch (cleared on read)
+
+__device__ __forceinline__ void l2_prefetch_slice(Prefetch pf) {
+  if (pf.bytes == 0 || threadIdx.x != 0) return;
+  const unsigned long long nblk = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+  const unsigned long long bid = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+  unsigned long long per = (pf.bytes + nblk - 1) / nblk;
+  per = (per + 127ull) & ~127ull;
+  const unsigned long long off = bid * per;
+  if (off >= pf.bytes) return;
+  unsigned long long n = pf.bytes - off;
+  n = (n < per ? n : per) & ~15ull;
+  if (n == 0) return;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(pf.ptr + off), "r"((unsigned)n) : "memory");
 }
 __device__ __forceinline__ uint4 ldg_cached(const void* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));

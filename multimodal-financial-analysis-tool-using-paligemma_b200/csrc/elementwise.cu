@@ -10,6 +10,13 @@ namespace pg {
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
+static thread_local Prefetch g_prefetch = {nullptr, 0};
+
+Prefetch take_prefetch() {
+  Prefetch p = g_prefetch;
+  g_prefetch = {nullptr, 0};
+  return p;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -274,6 +281,12 @@ extern "C" {
 const char* pg_last_error(void) { return g_err; }
 int pg_abi_version(void) { return 1; }
 unsigned long long pg_launch_count(void) { return g_launches.load(); }
+
+int pg_set_next_prefetch(const void* ptr, long long bytes) {
+  PG_REQUIRE(bytes >= 0 && ((uintptr_t)ptr % 16) == 0, "set_next_prefetch: region must be 16-byte aligned");
+  g_prefetch = {(const char*)ptr, (unsigned long long)(ptr ? bytes : 0)};
+  return PG_OK;
+}
 
 int pg_embed_merge(void* out, const int64_t* ids, const void* emb, const void* img_feats, int n_tokens,
                    int D, int64_t vocab, int64_t image_token_id, int64_t pad_id, int n_img_rows,

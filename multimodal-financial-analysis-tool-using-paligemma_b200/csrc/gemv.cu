@@ -2,6 +2,8 @@
 // step with 128-bit loads, fp32 accumulation, and the reference's elementwise neighbours fused
 // in: RMSNorm prologue, RoPE + KV-append / GeGLU / residual / logits+argmax epilogues.
 // HBM-bound: bytes per step = the weight bytes.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pg {
@@ -109,8 +111,10 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
                   const T* __restrict__ W, const float* __restrict__ inv_freq,
                   const int32_t* __restrict__ positions, T* __restrict__ k_pool, T* __restrict__ v_pool,
                   const int32_t* __restrict__ page_table, int pt_stride, int page_size,
-                  const int32_t* __restrict__ kv_len, int D, int nq, int nkv, int hd, float eps, int max_pos) {
+                  const int32_t* __restrict__ kv_len, int D, int nq, int nkv, int hd, float eps, int max_pos,
+                  Prefetch pf) {
   extern __shared__ __align__(16) float xs[];
+  l2_prefetch_slice(pf);
   norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GEMV_WARPS;
@@ -163,8 +167,9 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
 template <typename T, int NB, int KS>
 __global__ void __launch_bounds__(GEMV_THREADS)
 gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ W, const T* __restrict__ R,
-                int N, int K) {
+                int N, int K, Prefetch pf) {
   constexpr int V = Vec<T>::N;
+  l2_prefetch_slice(pf);
   constexpr int ROWS_PER_CTA = GEMV_WARPS / KS;
   __shared__ float part[GEMV_WARPS][NB];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -216,8 +221,9 @@ gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restric
 template <typename T, int NB>
 __global__ void __launch_bounds__(GEMV_THREADS)
 decode_gateup_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ norm_w,
-                     const T* __restrict__ W, int D, int F, float eps) {
+                     const T* __restrict__ W, int D, int F, float eps, Prefetch pf) {
   extern __shared__ __align__(16) float xs[];
+  l2_prefetch_slice(pf);
   norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GEMV_WARPS;
@@ -243,9 +249,11 @@ decode_gateup_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __re
 template <typename T, int NB>
 __global__ void __launch_bounds__(GEMV_THREADS)
 decode_lmhead_kernel(float* __restrict__ logits, const T* __restrict__ x, const T* __restrict__ norm_w,
-                     const T* __restrict__ W, int D, long long V, float eps, unsigned long long* keys) {
+                     const T* __restrict__ W, int D, long long V, float eps, unsigned long long* keys,
+                     Prefetch pf) {
   extern __shared__ __align__(16) float xs[];
   __shared__ unsigned long long best_s[GEMV_WARPS][NB];
+  l2_prefetch_slice(pf);
   norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * GEMV_WARPS + wid, nwarps = (long long)gridDim.x * GEMV_WARPS;
@@ -304,9 +312,14 @@ static int dispatch_nb(int B, F&& f) {
   return PG_ERR_INVALID;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 static int grid_for_units(long long units, int per_cta) {
   long long g = (units + per_cta - 1) / per_cta;
-  const long long cap = 148 * 2;
+  static const long long cap = 148LL * env_int("PG_GEMV_CTAS_PER_SM", 2);
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -332,6 +345,7 @@ int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_
                   const int32_t* positions, void* k_pool, void* v_pool, const int32_t* page_table,
                   int pt_stride, int page_size, const int32_t* kv_len, int B, int D, int nq, int nkv, int hd,
                   float eps, int max_pos, int dtype, void* stream) {
+  const Prefetch pf = take_prefetch();
   PG_REQUIRE(hd % 2 == 0, "decode_qkv: odd head_dim");
   const int units = (nq + 2 * nkv) * (hd / 2);
   PG_DISPATCH_DTYPE(dtype, T, {
@@ -344,7 +358,7 @@ int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_
       if (int e = set_smem(kern, smem)) return e;
       kern<<<grid_for_units(units, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
           (T*)q_out, (const T*)x, (const T*)norm_w, (const T*)w_qkv, inv_freq, positions, (T*)k_pool,
-          (T*)v_pool, page_table, pt_stride, page_size, kv_len, D, nq, nkv, hd, eps, max_pos);
+          (T*)v_pool, page_table, pt_stride, page_size, kv_len, D, nq, nkv, hd, eps, max_pos, pf);
       return check_launch("decode_qkv");
     });
   });
@@ -353,19 +367,31 @@ int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_
 
 int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, int N, int K, int dtype,
                 void* stream) {
+  const Prefetch pf = take_prefetch();
   PG_DISPATCH_DTYPE(dtype, T, {
     PG_REQUIRE(K % Vec<T>::N == 0, "gemv_res: K=%d not vector aligned", K);
     return dispatch_nb(B, [&](auto nb) {
       constexpr int NB = decltype(nb)::value;
-      if (K >= 8192) {
+      static const int ks_big = env_int("PG_DOWN_KS", 4);
+      if (K >= 8192 && ks_big == 8) {
+        constexpr int KS = 8;
+        int iters = cdiv(N, GEMV_WARPS / KS);
+        gemv_res_kernel<T, NB, KS><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
+            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf);
+      } else if (K >= 8192 && ks_big == 2) {
+        constexpr int KS = 2;
+        int iters = cdiv(N, GEMV_WARPS / KS);
+        gemv_res_kernel<T, NB, KS><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
+            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf);
+      } else if (K >= 8192) {
         constexpr int KS = 4;
         int iters = cdiv(N, GEMV_WARPS / KS);
         gemv_res_kernel<T, NB, KS><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
-            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K);
+            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf);
       } else {
         int iters = cdiv(N, GEMV_WARPS);
         gemv_res_kernel<T, NB, 1><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
-            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K);
+            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf);
       }
       return check_launch("gemv_res");
     });
@@ -375,6 +401,7 @@ int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, i
 
 int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w_gu, int B, int D, int F,
                      float eps, int dtype, void* stream) {
+  const Prefetch pf = take_prefetch();
   PG_DISPATCH_DTYPE(dtype, T, {
     PG_REQUIRE(D % Vec<T>::N == 0, "decode_gateup: D=%d not vector aligned", D);
     return dispatch_nb(B, [&](auto nb) {
@@ -384,7 +411,7 @@ int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w
       auto kern = decode_gateup_kernel<T, NB>;
       if (int e = set_smem(kern, smem)) return e;
       kern<<<grid_for_units(F, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
-          (T*)out, (const T*)x, (const T*)norm_w, (const T*)w_gu, D, F, eps);
+          (T*)out, (const T*)x, (const T*)norm_w, (const T*)w_gu, D, F, eps, pf);
       return check_launch("decode_gateup");
     });
   });
@@ -393,6 +420,7 @@ int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w
 
 int pg_decode_lmhead(float* logits, const void* x, const void* norm_w, const void* w_emb, int B, int D,
                      int64_t V, float eps, unsigned long long* argmax_keys, int dtype, void* stream) {
+  const Prefetch pf = take_prefetch();
   PG_DISPATCH_DTYPE(dtype, T, {
     PG_REQUIRE(D % Vec<T>::N == 0, "decode_lmhead: D=%d not vector aligned", D);
     return dispatch_nb(B, [&](auto nb) {
@@ -402,7 +430,7 @@ int pg_decode_lmhead(float* logits, const void* x, const void* norm_w, const voi
       auto kern = decode_lmhead_kernel<T, NB>;
       if (int e = set_smem(kern, smem)) return e;
       kern<<<grid_for_units((V + 1) / 2, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
-          logits, (const T*)x, (const T*)norm_w, (const T*)w_emb, D, (long long)V, eps, argmax_keys);
+          logits, (const T*)x, (const T*)norm_w, (const T*)w_emb, D, (long long)V, eps, argmax_keys, pf);
       return check_launch("decode_lmhead");
     });
   });

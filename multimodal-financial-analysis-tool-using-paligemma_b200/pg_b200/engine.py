@@ -15,6 +15,7 @@ float (Q9); RoPE inv_freq is rounded to the model dtype by `model.to(dtype)`.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Mapping, Optional
 
@@ -396,13 +397,25 @@ class DecodeState:
         self.ws = torch.zeros(int(nws), dtype=torch.float32, device=dev)
         self.counters = torch.zeros(batch * d.nkv, dtype=torch.int32, device=dev)
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.pf_cap_mb = float(os.environ.get("PG_PF_MB", "32"))   # L2 prefetch distance per launch (0 = off)
         self.kv: Optional[PagedKV] = None
         self.kv_table_ptr = None
+
+    def _pf(self, t: Optional[torch.Tensor], start_mb: float = 0.0, cap_mb: Optional[float] = None) -> None:
+        """Hand the next launch a weight region to pull into L2 (pg_set_next_prefetch)."""
+        if t is None or self.pf_cap_mb <= 0:
+            return
+        nbytes = t.numel() * t.element_size()
+        off = min(int(start_mb * (1 << 20)), nbytes) & ~127
+        n = min(nbytes - off, int((self.pf_cap_mb if cap_mb is None else cap_mb) * (1 << 20))) & ~15
+        if n > 0:
+            cabi.check(cabi.lib().pg_set_next_prefetch(t.data_ptr() + off, n), "set_next_prefetch")
 
     # one decode step: kernels only, no host sync, capturable
     def launch_step(self, kv: PagedKV, sample: Optional[tuple] = None, advance: bool = True) -> None:
         eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
         B, dt = self.B, self.eng.dt
+        cap = self.pf_cap_mb
         cabi.check(L.pg_embed_merge(ptr(self.x), ptr(self.ids), ptr(eng.emb), None, B, d.D, d.V,
                                     d.image_token_index, d.pad_token_id, 0, eng.img_div, eng.normalizer,
                                     ptr(eng.err_flag), dt, st), "embed")
@@ -411,24 +424,34 @@ class DecodeState:
         x, x2 = self.x, self.x2
         for li, w in enumerate(eng.t_layers):
             kp, vp = eng.k_pool[li], eng.v_pool[li]
+            nxt = eng.t_layers[li + 1]["qkv"] if li + 1 < len(eng.t_layers) else eng.lm_head
+            self._pf(w["o"])                                   # qkv pulls o_proj's weights
             for b0 in range(0, B, MB):
                 nb = min(MB, B - b0)
                 cabi.check(L.pg_decode_qkv(ptr(self.q[b0:]), ptr(x[b0:]), ptr(w["ln1"]), ptr(w["qkv"]), ptr(eng.inv_freq),
                                            ptr(self.pos[b0:]), ptr(kp), ptr(vp), ptr(kv.page_table[b0:]), kv.max_pages,
                                            eng.page_size, ptr(kv.kv_len[b0:]), nb, d.D, d.nq, d.nkv, d.hd, d.eps,
                                            d.max_pos, dt, st), "decode_qkv")
+            self._pf(w["gu"])                                  # attention pulls the head of gate/up
             cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
                                              kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, d.nq, d.nkv, d.hd,
                                              scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
                        "decode_attention")
             for b0 in range(0, B, MB):
                 nb = min(MB, B - b0)
+                if b0 == 0:
+                    self._pf(w["gu"], start_mb=cap)            # o_proj pulls the next slice of gate/up
                 cabi.check(L.pg_gemv_res(ptr(x2[b0:]), ptr(self.att[b0:]), ptr(w["o"]), ptr(x[b0:]), nb, d.D,
                                          d.nq * d.hd, dt, st), "o_proj")
+                if b0 == 0:
+                    self._pf(w["down"], cap_mb=1.5 * cap)      # gate/up pulls the head of down_proj
                 cabi.check(L.pg_decode_gateup(ptr(self.g[b0:]), ptr(x2[b0:]), ptr(w["ln2"]), ptr(w["gu"]), nb, d.D,
                                               d.F, d.eps, dt, st), "gateup")
+                if b0 == 0:
+                    self._pf(nxt, cap_mb=1.5 * cap)            # down_proj pulls the next layer's qkv / lm_head
                 cabi.check(L.pg_gemv_res(ptr(x[b0:]), ptr(self.g[b0:]), ptr(w["down"]), ptr(x2[b0:]), nb, d.D, d.F,
                                          dt, st), "down_proj")
+        self._pf(eng.t_layers[0]["qkv"])                       # lm_head pulls layer 0 for the next step
         for b0 in range(0, B, MB):
             nb = min(MB, B - b0)
             cabi.check(L.pg_decode_lmhead(ptr(self.logits[b0:]), ptr(x[b0:]), ptr(eng.final_norm), ptr(eng.lm_head),
