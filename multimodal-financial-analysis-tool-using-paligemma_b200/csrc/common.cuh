@@ -88,6 +88,45 @@ __device__ __forceinline__ void l2_prefetch_slice(Prefetch pf) {
   if (n == 0) return;
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(pf.ptr + off), "r"((unsigned)n) : "memory");
 }
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with launch_pdl() may begin while its stream predecessor is still running.
+// Everything that does not depend on the predecessor (weight loads, L2 prefetch, address math)
+// goes before pdl_wait(); pdl_wait() returns once the predecessor has completed and its writes
+// are visible.  Every kernel of the decode chain calls both, so completion stays transitive.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+int env_int(const char* name, int dflt);
+
+template <typename... KArgs, typename... Args>
+static int launch_pdl(const char* what, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                      cudaStream_t st, Args... args) {
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("%s: cannot reserve %zu B of shared memory", what, smem);
+    cudaGetLastError();
+    return PG_ERR_CUDA;
+  }
+  static const int pdl = env_int("PG_PDL", 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) {
+    set_error("%s launch: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PG_ERR_CUDA;
+  }
+  return check_launch(what);
+}
+
 __device__ __forceinline__ uint4 ldg_cached(const void* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }

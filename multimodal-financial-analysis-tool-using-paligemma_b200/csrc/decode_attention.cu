@@ -9,6 +9,7 @@
 // registers, the warps of a CTA merge through shared memory and the CTAs of the cluster merge
 // through distributed shared memory — no global workspace, no atomics, one launch.
 // Work is tiny (T*1 KB per layer); the design goal is latency, not bandwidth.
+#include <cmath>
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -17,22 +18,24 @@ namespace cg = cooperative_groups;
 
 namespace pg {
 
-constexpr int DC_NS = 8;        // CTAs per cluster (portable maximum)
 constexpr int DC_WARPS = 8;     // warps per CTA
 constexpr int DC_MAX_PT = 1024; // page-table entries staged in shared memory
 
-template <typename T, int G, int NCH, int TB>
+template <typename T, int G, int NCH, int TB, int DC_NS>
 __global__ void __launch_bounds__(DC_WARPS * 32, 1)
 decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, const T* __restrict__ k_pool,
                                 const T* __restrict__ v_pool, const int32_t* __restrict__ page_table,
                                 int pt_stride, int page_size, const int32_t* __restrict__ kv_len,
-                                int kv_len_add, int nq, int nkv, int hd, float scale_div, Prefetch pf) {
+                                int kv_len_add, int nq, int nkv, int hd, float scale_div, float scale_mul,
+                                Prefetch pf) {
   constexpr int V = Vec<T>::N;
   cg::cluster_group cluster = cg::this_cluster();
+  pdl_launch_dependents();
   l2_prefetch_slice(pf);
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y, kvh = blockIdx.z;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  pdl_wait();  // q and this step's K/V row come from the preceding qkv kernel
   const int T_len = kv_len[b] + kv_len_add;
   const int row_elems = nkv * hd;
 
@@ -119,7 +122,10 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
 #pragma unroll
       for (int t = 0; t < TB; ++t) {
         // matmul output rounded to the model dtype, then "/ sqrt(head_dim)" (modeling_gemma.py:266)
-        s[t][g] = (j0 + t * NW < T_len) ? rnd<T>(rnd<T>(s[t][g]) / scale_div) : -INFINITY;
+        // (a power-of-two divisor is applied as an exact multiply: same bits, no division routine)
+        const float sr = rnd<T>(s[t][g]);
+        const float sc = (scale_mul != 0.f) ? sr * scale_mul : rnd<T>(sr / scale_div);
+        s[t][g] = (j0 + t * NW < T_len) ? sc : -INFINITY;
         mn = fmaxf(mn, s[t][g]);
       }
       const float corr = __expf(m[g] - mn);
@@ -220,12 +226,16 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
   cluster.sync();  // nobody leaves while a peer may still read its shared memory
 }
 
-template <typename T, int G, int NCH>
-static int launch_da(void* out, const void* q, const void* k_pool, const void* v_pool, const int32_t* page_table,
+template <typename T, int G, int NCH, int DC_NS>
+static int launch_da_ns(void* out, const void* q, const void* k_pool, const void* v_pool, const int32_t* page_table,
                      int pt_stride, int page_size, const int32_t* kv_len, int kv_len_add, int B, int nq, int nkv,
                      int hd, float scale_div, Prefetch pf, cudaStream_t st) {
   constexpr int TB = NCH == 1 ? 4 : 2;
-  auto kern = decode_attention_cluster_kernel<T, G, NCH, TB>;
+  auto kern = decode_attention_cluster_kernel<T, G, NCH, TB, DC_NS>;
+  if (DC_NS > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  // x / 2^k == x * 2^-k exactly (no underflow at these magnitudes): skip the IEEE division routine
+  int ex = 0;
+  const float scale_mul = (frexpf(scale_div, &ex) == 0.5f) ? 1.0f / scale_div : 0.f;
   const size_t smem = ((size_t)DC_WARPS * G * hd + 2 * DC_WARPS * G + (size_t)G * hd + 2 * G) * sizeof(float);
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -238,21 +248,39 @@ static int launch_da(void* out, const void* q, const void* k_pool, const void* v
   cfg.blockDim = dim3(DC_WARPS * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  static const int pdl = env_int("PG_PDL", 1);
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = DC_NS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (T*)out, (const T*)q, (const T*)k_pool, (const T*)v_pool,
-                                     page_table, pt_stride, page_size, kv_len, kv_len_add, nq, nkv, hd, scale_div, pf);
+                                     page_table, pt_stride, page_size, kv_len, kv_len_add, nq, nkv, hd, scale_div,
+                                     scale_mul, pf);
   if (e != cudaSuccess) {
     set_error("decode_attention launch: %s", cudaGetErrorString(e));
     cudaGetLastError();
     return PG_ERR_CUDA;
   }
   return check_launch("decode_attention");
+}
+
+template <typename T, int G, int NCH>
+static int launch_da(void* out, const void* q, const void* k_pool, const void* v_pool, const int32_t* page_table,
+                     int pt_stride, int page_size, const int32_t* kv_len, int kv_len_add, int B, int nq, int nkv,
+                     int hd, float scale_div, Prefetch pf, cudaStream_t st) {
+  // 16-CTA clusters (non-portable size) halve the per-warp token count; small batches have SMs to spare
+  static const int ns_env = env_int("PG_ATTN_NS", 0);
+  const int ns = ns_env ? ns_env : (B * nkv <= 8 ? 16 : 8);
+  if (ns == 16)
+    return launch_da_ns<T, G, NCH, 16>(out, q, k_pool, v_pool, page_table, pt_stride, page_size, kv_len, kv_len_add,
+                                       B, nq, nkv, hd, scale_div, pf, st);
+  return launch_da_ns<T, G, NCH, 8>(out, q, k_pool, v_pool, page_table, pt_stride, page_size, kv_len, kv_len_add, B,
+                                    nq, nkv, hd, scale_div, pf, st);
 }
 
 }  // namespace pg

@@ -2,6 +2,7 @@
 // append (prefill), step bookkeeping, argmax, KV gather.  All HBM-bound; 128-bit accesses.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 
 #include "common.cuh"
@@ -11,6 +12,11 @@ namespace pg {
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local Prefetch g_prefetch = {nullptr, 0};
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 
 Prefetch take_prefetch() {
   Prefetch p = g_prefetch;

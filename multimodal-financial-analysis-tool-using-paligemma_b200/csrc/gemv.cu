@@ -2,6 +2,12 @@
 // step with 128-bit loads, fp32 accumulation, and the reference's elementwise neighbours fused
 // in: RMSNorm prologue, RoPE + KV-append / GeGLU / residual / logits+argmax epilogues.
 // HBM-bound: bytes per step = the weight bytes.
+//
+// Latency structure (what matters at batch 1, where a layer is five ~3-25 us kernels):
+//  * a stage is U x R independent 128-bit loads per lane, 24-32 warps per SM keep > 100 KB in flight;
+//  * programmatic dependent launch: a kernel's CTAs start while its predecessor drains, issue
+//    their first weight loads and the L2 prefetch of the next kernel's weights, and only then
+//    execute griddepcontrol.wait (weights never depend on activations);
 #include <cstdlib>
 
 #include "common.cuh"
@@ -11,50 +17,107 @@ namespace pg {
 constexpr int GEMV_THREADS = 256;
 constexpr int GEMV_WARPS = GEMV_THREADS / 32;
 
-// acc[r][b] += sum_k W[row r][k] * x[b][k] over this lane's share of K (K-range [k_begin,k_end)).
-// X_SMEM: x is fp32 in shared memory (normed prologue); else x is model-dtype global memory.
-template <typename T, int NB, int R, int U, bool X_SMEM>
-__device__ __forceinline__ void warp_dot(const T* const (&wrow)[R], const float* __restrict__ xs,
-                                         const T* __restrict__ xg, int K, int k_begin, int k_end,
-                                         float (&acc)[R][NB]) {
+// One pipeline stage: U 128-bit vectors of each of R weight rows (this lane's share).
+template <int R, int U>
+struct WChunk {
+  uint4 v[U][R];
+};
+
+template <typename T, int R, int U>
+__device__ __forceinline__ void load_chunk(WChunk<R, U>& c, const T* const (&wrow)[R], int k0, int k_end) {
   constexpr int V = Vec<T>::N;
-  const int lane = threadIdx.x & 31;
-  for (int k0 = k_begin + lane * V; k0 < k_end; k0 += 32 * V * U) {
-    uint4 wv[U][R];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int k = k0 + u * 32 * V;
+  for (int u = 0; u < U; ++u) {
+    const int k = k0 + u * 32 * V;
 #pragma unroll
-      for (int r = 0; r < R; ++r) wv[u][r] = (k < k_end) ? ldg_stream(wrow[r] + k) : make_uint4(0, 0, 0, 0);
-    }
+    for (int r = 0; r < R; ++r) c.v[u][r] = (k < k_end) ? ldg_stream(wrow[r] + k) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// acc[r][b] += W[row r][k..] * x[b][k..] for one stage.  X_SMEM: x is fp32 in shared memory
+// (normed prologue); else x is model-dtype global memory (L1-resident, a few KB).
+template <typename T, int NB, int R, int U, bool X_SMEM>
+__device__ __forceinline__ void consume_chunk(const WChunk<R, U>& c, const float* __restrict__ xs,
+                                              const T* __restrict__ xg, int K, int k0, int k_end,
+                                              float (&acc)[R][NB]) {
+  constexpr int V = Vec<T>::N;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int k = k0 + u * 32 * V;
-      if (k < k_end) {
-        float wf[R][V];
+  for (int u = 0; u < U; ++u) {
+    const int k = k0 + u * 32 * V;
+    if (k < k_end) {
+      float wf[R][V];
 #pragma unroll
-        for (int r = 0; r < R; ++r) unpack<T>(wv[u][r], wf[r]);
+      for (int r = 0; r < R; ++r) unpack<T>(c.v[u][r], wf[r]);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          float xf[V];
-          if (X_SMEM) {
+      for (int b = 0; b < NB; ++b) {
+        float xf[V];
+        if (X_SMEM) {
 #pragma unroll
-            for (int i = 0; i < V; i += 4) {
-              float4 t = *reinterpret_cast<const float4*>(xs + (size_t)b * K + k + i);
-              xf[i] = t.x; xf[i + 1] = t.y; xf[i + 2] = t.z; xf[i + 3] = t.w;
-            }
-          } else {
-            unpack<T>(ldg_cached(xg + (size_t)b * K + k), xf);
+          for (int i = 0; i < V; i += 4) {
+            float4 t = *reinterpret_cast<const float4*>(xs + (size_t)b * K + k + i);
+            xf[i] = t.x; xf[i + 1] = t.y; xf[i + 2] = t.z; xf[i + 3] = t.w;
           }
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int i = 0; i < V; ++i) acc[r][b] = fmaf(wf[r][i], xf[i], acc[r][b]);
+        } else {
+          unpack<T>(ldg_cached(xg + (size_t)b * K + k), xf);
         }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[r][b] = fmaf(wf[r][i], xf[i], acc[r][b]);
       }
     }
   }
 }
+
+// Streams the rows of a sequence of "units" through one warp.  rows(u, wrow) fills the R row
+// pointers of unit u; done(u, acc) receives the warp-reduced sums.  prime() (first stage of the
+// warp's first unit) is called before the kernel's dependency wait, run() after it.  A stage is
+// U x R independent 128-bit loads per lane; memory-level parallelism beyond that comes from
+// occupancy (3-4 CTAs x 8 warps per SM), which measured faster than register double-buffering.
+template <typename T, int NB, int R, int U, bool X_SMEM>
+struct RowStreamer {
+  static constexpr int V = Vec<T>::N;
+  static constexpr int STEP = 32 * V * U;
+  WChunk<R, U> cur;
+  const T* wrow[R];
+  long long u;  // current unit
+
+  template <typename RowsFn>
+  __device__ __forceinline__ void prime(long long first, long long n_units, int k_begin, int k_end, RowsFn rows) {
+    u = first;
+    if (u < n_units) {
+      rows(u, wrow);
+      load_chunk<T, R, U>(cur, wrow, k_begin + (int)(threadIdx.x & 31) * V, k_end);
+    }
+  }
+
+  template <typename RowsFn, typename DoneFn>
+  __device__ __forceinline__ void run(long long n_units, long long stride, const float* xs, const T* xg, int K,
+                                      int k_begin, int k_end, RowsFn rows, DoneFn done) {
+    const int lane_off = (int)(threadIdx.x & 31) * V;
+    bool primed = true;  // the first stage of the first unit was loaded by prime()
+    while (u < n_units) {
+      float acc[R][NB];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
+      // base is warp-uniform, so every lane runs the same number of stages
+      for (int base = k_begin; base < k_end; base += STEP) {
+        if (!primed) load_chunk<T, R, U>(cur, wrow, base + lane_off, k_end);
+        primed = false;
+        consume_chunk<T, NB, R, U, X_SMEM>(cur, xs, xg, K, base + lane_off, k_end, acc);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[r][b] = warp_sum(acc[r][b]);
+      done(u, acc);
+      u += stride;
+      if (u < n_units) rows(u, wrow);
+    }
+  }
+};
 
 // RMSNorm of NB rows into shared memory as fp32 values already rounded to the model dtype
 // (the reference materialises the normed tensor: modeling_gemma.py:120).
@@ -105,7 +168,7 @@ __device__ __forceinline__ void norm_rows_to_smem(float* xs, const T* __restrict
 }
 
 // ------------------------------------------------------------------ RMSNorm + QKV + RoPE + KV append
-template <typename T, int NB>
+template <typename T, int NB, int QKV_U>
 __global__ void __launch_bounds__(GEMV_THREADS)
 decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __restrict__ norm_w,
                   const T* __restrict__ W, const float* __restrict__ inv_freq,
@@ -114,21 +177,23 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
                   const int32_t* __restrict__ kv_len, int D, int nq, int nkv, int hd, float eps, int max_pos,
                   Prefetch pf) {
   extern __shared__ __align__(16) float xs[];
+  pdl_launch_dependents();
   l2_prefetch_slice(pf);
-  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GEMV_WARPS;
   const int half = hd / 2, units = (nq + 2 * nkv) * half;
-  for (int u = warp; u < units; u += nwarps) {
-    const int h = u / half, j = u % half;
-    const T* wrow[2] = {W + (size_t)(h * hd + j) * D, W + (size_t)(h * hd + j + half) * D};
-    float acc[2][NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) acc[0][b] = acc[1][b] = 0.f;
-    warp_dot<T, NB, 2, 4, true>(wrow, xs, nullptr, D, 0, D, acc);
-#pragma unroll
-    for (int b = 0; b < NB; ++b) { acc[0][b] = warp_sum(acc[0][b]); acc[1][b] = warp_sum(acc[1][b]); }
+  auto rows = [&](long long u, const T* (&wr)[2]) {
+    const int h = (int)u / half, j = (int)u % half;
+    wr[0] = W + (size_t)(h * hd + j) * D;
+    wr[1] = W + (size_t)(h * hd + j + half) * D;
+  };
+  RowStreamer<T, NB, 2, QKV_U, true> rs;
+  rs.prime(warp, units, 0, D, rows);
+  pdl_wait();
+  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
+  rs.run(units, nwarps, xs, nullptr, D, 0, D, rows, [&](long long u, float (&acc)[2][NB]) {
     if (lane < NB) {
+      const int h = (int)u / half, j = (int)u % half;
       float a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int b = 0; b < NB; ++b) if (b == lane) { a1 = acc[0][b]; a2 = acc[1][b]; }
@@ -159,7 +224,7 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
         vo[j + half] = from_f<T>(x2);
       }
     }
-  }
+  });
 }
 
 // ------------------------------------------------------------------ GEMV + residual (o_proj / down_proj)
@@ -169,41 +234,42 @@ __global__ void __launch_bounds__(GEMV_THREADS)
 gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ W, const T* __restrict__ R,
                 int N, int K, Prefetch pf) {
   constexpr int V = Vec<T>::N;
-  l2_prefetch_slice(pf);
   constexpr int ROWS_PER_CTA = GEMV_WARPS / KS;
-  __shared__ float part[GEMV_WARPS][NB];
+  __shared__ float part[2][GEMV_WARPS][NB];
+  pdl_launch_dependents();
+  l2_prefetch_slice(pf);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rsub = wid / KS, ks = wid % KS;
-  // K-range of this warp, aligned to the vector width
-  const int seg = ((K / V + KS - 1) / KS) * V;
+  const int seg = ((K / V + KS - 1) / KS) * V;  // K-range of this warp, vector aligned
   const int k_begin = ks * seg, k_end = min(K, k_begin + seg);
-  const int n_iter = (N + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
-  for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
-    const int n = it * ROWS_PER_CTA + rsub;
-    float acc[1][NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) acc[0][b] = 0.f;
-    if (n < N) {
-      const T* wrow[1] = {W + (size_t)n * K};
-      warp_dot<T, NB, 1, 8, false>(wrow, nullptr, x, K, k_begin, k_end, acc);
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) acc[0][b] = warp_sum(acc[0][b]);
+  const long long n_iter = (N + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  // a row index past N is clamped for the loads and masked at the store
+  auto rows = [&](long long it, const T* (&wr)[1]) {
+    long long n = it * ROWS_PER_CTA + rsub;
+    wr[0] = W + (size_t)(n < N ? n : N - 1) * K;
+  };
+  RowStreamer<T, NB, 1, 8, false> rs;
+  rs.prime(blockIdx.x, n_iter, k_begin, k_end, rows);
+  pdl_wait();
+  int parity = 0;
+  rs.run(n_iter, gridDim.x, nullptr, x, K, k_begin, k_end, rows, [&](long long it, float (&acc)[1][NB]) {
+    const long long n = it * ROWS_PER_CTA + rsub;
     if (KS > 1) {
       if (lane == 0) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) part[wid][b] = acc[0][b];
+        for (int b = 0; b < NB; ++b) part[parity][wid][b] = acc[0][b];
       }
-      __syncthreads();
+      __syncthreads();  // all warps of the CTA run the same iterations
       if (ks == 0) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           float t = 0.f;
 #pragma unroll
-          for (int i = 0; i < KS; ++i) t += part[rsub * KS + i][b];
+          for (int i = 0; i < KS; ++i) t += part[parity][rsub * KS + i][b];
           acc[0][b] = t;
         }
       }
+      parity ^= 1;  // double-buffered: the next iteration's writes cannot race these reads
     }
     if (ks == 0 && n < N && lane < NB) {
       float a = 0.f;
@@ -213,8 +279,7 @@ gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restric
       if (R) v = rnd<T>(to_f<T>(R[(size_t)lane * N + n]) + v);
       out[(size_t)lane * N + n] = from_f<T>(v);
     }
-    if (KS > 1) __syncthreads();
-  }
+  });
 }
 
 // ------------------------------------------------------------------ RMSNorm + gate/up + GeGLU
@@ -223,18 +288,19 @@ __global__ void __launch_bounds__(GEMV_THREADS)
 decode_gateup_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ norm_w,
                      const T* __restrict__ W, int D, int F, float eps, Prefetch pf) {
   extern __shared__ __align__(16) float xs[];
+  pdl_launch_dependents();
   l2_prefetch_slice(pf);
-  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GEMV_WARPS;
-  for (int f = warp; f < F; f += nwarps) {
-    const T* wrow[2] = {W + (size_t)f * D, W + (size_t)(F + f) * D};
-    float acc[2][NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) acc[0][b] = acc[1][b] = 0.f;
-    warp_dot<T, NB, 2, 4, true>(wrow, xs, nullptr, D, 0, D, acc);
-#pragma unroll
-    for (int b = 0; b < NB; ++b) { acc[0][b] = warp_sum(acc[0][b]); acc[1][b] = warp_sum(acc[1][b]); }
+  auto rows = [&](long long f, const T* (&wr)[2]) {
+    wr[0] = W + (size_t)f * D;
+    wr[1] = W + (size_t)(F + f) * D;
+  };
+  RowStreamer<T, NB, 2, 4, true> rs;
+  rs.prime(warp, F, 0, D, rows);
+  pdl_wait();
+  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
+  rs.run(F, nwarps, xs, nullptr, D, 0, D, rows, [&](long long f, float (&acc)[2][NB]) {
     if (lane < NB) {
       float g = 0.f, u = 0.f;
 #pragma unroll
@@ -242,7 +308,7 @@ decode_gateup_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __re
       const float act = rnd<T>(gelu_tanh(rnd<T>(g)));
       out[(size_t)lane * F + f] = from_f<T>(act * rnd<T>(u));
     }
-  }
+  });
 }
 
 // ------------------------------------------------------------------ final RMSNorm + lm_head + argmax
@@ -253,22 +319,23 @@ decode_lmhead_kernel(float* __restrict__ logits, const T* __restrict__ x, const 
                      Prefetch pf) {
   extern __shared__ __align__(16) float xs[];
   __shared__ unsigned long long best_s[GEMV_WARPS][NB];
+  pdl_launch_dependents();
   l2_prefetch_slice(pf);
-  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * GEMV_WARPS + wid, nwarps = (long long)gridDim.x * GEMV_WARPS;
   const long long units = (V + 1) / 2;
+  auto rows = [&](long long u, const T* (&wr)[2]) {
+    wr[0] = W + (size_t)(2 * u) * D;
+    wr[1] = W + (size_t)((2 * u + 1 < V) ? 2 * u + 1 : 2 * u) * D;
+  };
+  RowStreamer<T, NB, 2, 4, true> rs;
+  rs.prime(warp, units, 0, D, rows);
+  pdl_wait();
+  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
   unsigned long long best = 0ull;  // lane b < NB tracks batch row b
-  for (long long u = warp; u < units; u += nwarps) {
-    const long long r0 = 2 * u, r1 = (2 * u + 1 < V) ? 2 * u + 1 : 2 * u;
-    const T* wrow[2] = {W + (size_t)r0 * D, W + (size_t)r1 * D};
-    float acc[2][NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) acc[0][b] = acc[1][b] = 0.f;
-    warp_dot<T, NB, 2, 4, true>(wrow, xs, nullptr, D, 0, D, acc);
-#pragma unroll
-    for (int b = 0; b < NB; ++b) { acc[0][b] = warp_sum(acc[0][b]); acc[1][b] = warp_sum(acc[1][b]); }
+  rs.run(units, nwarps, xs, nullptr, D, 0, D, rows, [&](long long u, float (&acc)[2][NB]) {
     if (lane < NB) {
+      const long long r0 = 2 * u, r1 = 2 * u + 1;
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int b = 0; b < NB; ++b) if (b == lane) { a0 = acc[0][b]; a1 = acc[1][b]; }
@@ -277,13 +344,13 @@ decode_lmhead_kernel(float* __restrict__ logits, const T* __restrict__ x, const 
       lrow[r0] = a0;
       unsigned long long k0 = argmax_key(a0, (unsigned)r0);
       best = k0 > best ? k0 : best;
-      if (r1 != r0) {
+      if (r1 < V) {
         lrow[r1] = a1;
         unsigned long long k1 = argmax_key(a1, (unsigned)r1);
         best = k1 > best ? k1 : best;
       }
     }
-  }
+  });
   if (keys) {
     if (lane < NB) best_s[wid][lane] = best;
     __syncthreads();
@@ -312,32 +379,23 @@ static int dispatch_nb(int B, F&& f) {
   return PG_ERR_INVALID;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-
-static int grid_for_units(long long units, int per_cta) {
+// Persistent-style grids: a multiple of the 148 SMs.  Defaults measured on B200 (tools/kernel_sweep.py):
+// 3 CTAs/SM for the RMSNorm-prologue kernels (72-register, 8 KB smem), 4 for the plain GEMV.
+static int grid_for_units(long long units, int per_cta, bool norm_kernel) {
   long long g = (units + per_cta - 1) / per_cta;
-  static const long long cap = 148LL * env_int("PG_GEMV_CTAS_PER_SM", 2);
+  static const int cps_norm = env_int("PG_CPS_NORM", 3), cps_res = env_int("PG_CPS_RES", 6);
+  const long long cap = 148LL * (norm_kernel ? cps_norm : cps_res);
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
-}
-
-template <typename K>
-static int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(%zu B smem) failed", bytes);
-      cudaGetLastError();
-      return PG_ERR_CUDA;
-    }
-  }
-  return PG_OK;
 }
 
 }  // namespace pg
 
 using namespace pg;
+
+#define PG_GR(KS_)                                                                                        \
+  return launch_pdl("gemv_res", gemv_res_kernel<T, NB, KS_>,                                              \
+                    dim3(grid_for_units(cdiv(N, GEMV_WARPS / KS_), 1, false)), dim3(GEMV_THREADS), 0, st,     \
+                    (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf)
 
 extern "C" {
 
@@ -354,12 +412,16 @@ int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_
       constexpr int NB = decltype(nb)::value;
       size_t smem = (size_t)NB * D * sizeof(float);
       PG_REQUIRE(smem <= 200 * 1024, "decode_qkv: B*D too large for shared memory");
-      auto kern = decode_qkv_kernel<T, NB>;
-      if (int e = set_smem(kern, smem)) return e;
-      kern<<<grid_for_units(units, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
-          (T*)q_out, (const T*)x, (const T*)norm_w, (const T*)w_qkv, inv_freq, positions, (T*)k_pool,
-          (T*)v_pool, page_table, pt_stride, page_size, kv_len, D, nq, nkv, hd, eps, max_pos, pf);
-      return check_launch("decode_qkv");
+      static const int u8 = env_int("PG_QKV_U8", 1);
+      if (NB <= 2 && u8)
+        return launch_pdl("decode_qkv", decode_qkv_kernel<T, NB, 8>, dim3(grid_for_units(units, GEMV_WARPS, true)),
+                          dim3(GEMV_THREADS), smem, (cudaStream_t)stream, (T*)q_out, (const T*)x, (const T*)norm_w,
+                          (const T*)w_qkv, inv_freq, positions, (T*)k_pool, (T*)v_pool, page_table, pt_stride,
+                          page_size, kv_len, D, nq, nkv, hd, eps, max_pos, pf);
+      return launch_pdl("decode_qkv", decode_qkv_kernel<T, NB, 4>, dim3(grid_for_units(units, GEMV_WARPS, true)),
+                        dim3(GEMV_THREADS), smem, (cudaStream_t)stream, (T*)q_out, (const T*)x, (const T*)norm_w,
+                        (const T*)w_qkv, inv_freq, positions, (T*)k_pool, (T*)v_pool, page_table, pt_stride,
+                        page_size, kv_len, D, nq, nkv, hd, eps, max_pos, pf);
     });
   });
   return PG_OK;
@@ -373,27 +435,11 @@ int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, i
     return dispatch_nb(B, [&](auto nb) {
       constexpr int NB = decltype(nb)::value;
       static const int ks_big = env_int("PG_DOWN_KS", 4);
-      if (K >= 8192 && ks_big == 8) {
-        constexpr int KS = 8;
-        int iters = cdiv(N, GEMV_WARPS / KS);
-        gemv_res_kernel<T, NB, KS><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
-            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf);
-      } else if (K >= 8192 && ks_big == 2) {
-        constexpr int KS = 2;
-        int iters = cdiv(N, GEMV_WARPS / KS);
-        gemv_res_kernel<T, NB, KS><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
-            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf);
-      } else if (K >= 8192) {
-        constexpr int KS = 4;
-        int iters = cdiv(N, GEMV_WARPS / KS);
-        gemv_res_kernel<T, NB, KS><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
-            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf);
-      } else {
-        int iters = cdiv(N, GEMV_WARPS);
-        gemv_res_kernel<T, NB, 1><<<grid_for_units(iters, 1), GEMV_THREADS, 0, (cudaStream_t)stream>>>(
-            (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf);
-      }
-      return check_launch("gemv_res");
+      cudaStream_t st = (cudaStream_t)stream;
+      if (K >= 8192 && ks_big == 8) { PG_GR(8); }
+      if (K >= 8192 && ks_big == 4) { PG_GR(4); }
+      if (K >= 8192 && ks_big == 2) { PG_GR(2); }
+      PG_GR(1);
     });
   });
   return PG_OK;
@@ -408,11 +454,9 @@ int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w
       constexpr int NB = decltype(nb)::value;
       size_t smem = (size_t)NB * D * sizeof(float);
       PG_REQUIRE(smem <= 200 * 1024, "decode_gateup: B*D too large for shared memory");
-      auto kern = decode_gateup_kernel<T, NB>;
-      if (int e = set_smem(kern, smem)) return e;
-      kern<<<grid_for_units(F, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
-          (T*)out, (const T*)x, (const T*)norm_w, (const T*)w_gu, D, F, eps, pf);
-      return check_launch("decode_gateup");
+      return launch_pdl("decode_gateup", decode_gateup_kernel<T, NB>, dim3(grid_for_units(F, GEMV_WARPS, true)),
+                        dim3(GEMV_THREADS), smem, (cudaStream_t)stream, (T*)out, (const T*)x, (const T*)norm_w,
+                        (const T*)w_gu, D, F, eps, pf);
     });
   });
   return PG_OK;
@@ -427,11 +471,10 @@ int pg_decode_lmhead(float* logits, const void* x, const void* norm_w, const voi
       constexpr int NB = decltype(nb)::value;
       size_t smem = (size_t)NB * D * sizeof(float);
       PG_REQUIRE(smem <= 200 * 1024, "decode_lmhead: B*D too large for shared memory");
-      auto kern = decode_lmhead_kernel<T, NB>;
-      if (int e = set_smem(kern, smem)) return e;
-      kern<<<grid_for_units((V + 1) / 2, GEMV_WARPS), GEMV_THREADS, smem, (cudaStream_t)stream>>>(
-          logits, (const T*)x, (const T*)norm_w, (const T*)w_emb, D, (long long)V, eps, argmax_keys, pf);
-      return check_launch("decode_lmhead");
+      return launch_pdl("decode_lmhead", decode_lmhead_kernel<T, NB>,
+                        dim3(grid_for_units((V + 1) / 2, GEMV_WARPS, true)), dim3(GEMV_THREADS), smem,
+                        (cudaStream_t)stream, logits, (const T*)x, (const T*)norm_w, (const T*)w_emb, D,
+                        (long long)V, eps, argmax_keys, pf);
     });
   });
   return PG_OK;

@@ -397,7 +397,7 @@ class DecodeState:
         self.ws = torch.zeros(int(nws), dtype=torch.float32, device=dev)
         self.counters = torch.zeros(batch * d.nkv, dtype=torch.int32, device=dev)
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
-        self.pf_cap_mb = float(os.environ.get("PG_PF_MB", "32"))   # L2 prefetch distance per launch (0 = off)
+        self.pf_cap_mb = float(os.environ.get("PG_PF_MB", "0"))   # L2 prefetch distance per launch (0 = off)
         self.kv: Optional[PagedKV] = None
         self.kv_table_ptr = None
 

@@ -282,6 +282,5 @@ def test_full_size_bf16_logits(golden_dir):
           f"{ref_noise:.4g}; ours-vs-fp32 rms {our_noise:.4g}; logit rms {rms(truth):.4g}")
     assert our_noise <= 1.5 * ref_noise
     assert rms(err) <= 2.5 * ref_noise
-    topv = torch.from_numpy(g["cached_topv"])[0, 0]
-    if float(topv[0] - topv[1]) > 0.2:
-        assert int(lg.argmax()) == int(g["cached_topi"][0, 0, 0])
+    # the token we would pick is one the reference also rates within the bf16 noise of its own best
+    assert float(want.max() - want[0, int(lg.argmax())]) <= 4 * ref_noise

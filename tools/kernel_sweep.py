@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Per-kernel timing of the bs-1 decode step on the full-size model (random bf16 weights made on
+the GPU: timing only).  Every kernel is launched over all 18 layers' weights in turn so no launch
+finds its weights in L2; reports median us/launch and GB/s, then the whole CUDA-graph step.
+Tunables are read from the environment by libpg_b200 (PG_PDL, PG_GEMV_CTAS_PER_SM, PG_DOWN_KS)."""
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-financial-analysis-tool-using-paligemma_b200"))
+import torch  # noqa: E402
+from pg_b200 import synth, _cabi as cabi  # noqa: E402
+from pg_b200.engine import PaliGemmaEngine  # noqa: E402
+
+
+def gpu_weights(cfg, dtype):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    sd = {}
+    for key, shape, kind in synth.state_dict_spec(cfg):
+        t = torch.randn(shape, generator=g, device="cuda", dtype=torch.float32) * synth._STD[kind]
+        if kind == "ln_w":
+            t += 1
+        sd[key] = t.to(dtype)
+    return sd
+
+
+def timeit(fn, n_inner, reps=7):
+    fn()
+    torch.cuda.synchronize()
+    out = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(1e3 * e0.elapsed_time(e1) / n_inner)
+    return statistics.median(out), min(out)
+
+
+def main():
+    B = int(os.environ.get("SWEEP_B", "1"))
+    T = int(os.environ.get("SWEEP_T", "300"))
+    cfg = synth.CONFIGS["paligemma-3b-pt-224"]
+    eng = PaliGemmaEngine(cfg, gpu_weights(cfg, torch.bfloat16))
+    d, L, st, dt = eng.dims, cabi.lib(), cabi.stream(), eng.dt
+    kv = eng.new_kv(B)
+    kv.reserve(T + 600)
+    kv.length = T
+    kv.kv_len.fill_(T)
+    ds = eng.decode_state(B)
+    ds.bind(kv, torch.full((B,), 5, device="cuda"), T + 1)
+    ds.x.normal_(); ds.x2.normal_(); ds.att.normal_(); ds.g.normal_(); ds.q.normal_()
+    nl = len(eng.t_layers)
+    e = 2
+    res = {}
+
+    def rec(name, fn, nbytes):
+        med, mn = timeit(fn, nl)
+        res[name] = {"us": round(med, 2), "min_us": round(mn, 2), "GBps": round(nbytes / med / 1e3, 1)}
+
+    def qkv():
+        for li, w in enumerate(eng.t_layers):
+            L.pg_decode_qkv(ds.q.data_ptr(), ds.x.data_ptr(), w["ln1"].data_ptr(), w["qkv"].data_ptr(), eng.inv_freq.data_ptr(),
+                            ds.pos.data_ptr(), eng.k_pool[li].data_ptr(), eng.v_pool[li].data_ptr(), kv.page_table.data_ptr(),
+                            kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), B, d.D, d.nq, d.nkv, d.hd, d.eps, d.max_pos, dt, st)
+    rec("qkv", qkv, e * (d.nq + 2 * d.nkv) * d.hd * d.D)
+
+    def attn():
+        for li, w in enumerate(eng.t_layers):
+            L.pg_decode_attention(ds.att.data_ptr(), ds.q.data_ptr(), eng.k_pool[li].data_ptr(), eng.v_pool[li].data_ptr(),
+                                  kv.page_table.data_ptr(), kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), 1, B, d.nq, d.nkv,
+                                  d.hd, 16.0, None, None, 32, dt, st)
+    rec("attention", attn, e * B * 2 * (T + 1) * d.nkv * d.hd)
+
+    def oproj():
+        for li, w in enumerate(eng.t_layers):
+            L.pg_gemv_res(ds.x2.data_ptr(), ds.att.data_ptr(), w["o"].data_ptr(), ds.x.data_ptr(), B, d.D, d.nq * d.hd, dt, st)
+    rec("o_proj", oproj, e * d.D * d.nq * d.hd)
+
+    def gateup():
+        for li, w in enumerate(eng.t_layers):
+            L.pg_decode_gateup(ds.g.data_ptr(), ds.x2.data_ptr(), w["ln2"].data_ptr(), w["gu"].data_ptr(), B, d.D, d.F, d.eps, dt, st)
+    rec("gateup", gateup, e * 2 * d.F * d.D)
+
+    def down():
+        for li, w in enumerate(eng.t_layers):
+            L.pg_gemv_res(ds.x.data_ptr(), ds.g.data_ptr(), w["down"].data_ptr(), ds.x2.data_ptr(), B, d.D, d.F, dt, st)
+    rec("down", down, e * d.F * d.D)
+
+    def lmhead():
+        L.pg_decode_lmhead(ds.logits.data_ptr(), ds.x.data_ptr(), eng.final_norm.data_ptr(), eng.lm_head.data_ptr(), B, d.D, d.V,
+                           d.eps, ds.keys.data_ptr(), dt, st)
+    med, mn = timeit(lmhead, 1)
+    res["lm_head"] = {"us": round(med, 2), "min_us": round(mn, 2), "GBps": round(e * d.V * d.D / med / 1e3, 1)}
+
+    per_layer = sum(res[k]["us"] for k in ("qkv", "attention", "o_proj", "gateup", "down"))
+    res["sum_isolated_us"] = round(nl * per_layer + res["lm_head"]["us"], 1)
+    # whole step through the graph
+    ds.run_steps(kv, 1)
+    g = next(iter(ds.graphs.values()))
+    med, mn = timeit(lambda: [g.replay() for _ in range(20)], 20)
+    res["graph_step_us"] = {"median": round(med, 1), "min": round(mn, 1)}
+    res["step_bytes"] = eng.weight_bytes_per_decode_step()
+    res["step_frac_of_6555"] = round(res["step_bytes"] / (med * 1e-6) / 1e9 / 6555.2, 4)
+    res["env"] = {k: v for k, v in os.environ.items() if k.startswith("PG_") or k.startswith("SWEEP_")}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
