@@ -1,10 +1,349 @@
-// tcgen05 / TMEM / TMA GEMM — placeholder until the kernel lands; pg_gemm routes to SIMT.
+// C[M,N] = A[M,K] W[N,K]^T on the 5th-generation tensor cores: TMA (cp.async.bulk.tensor,
+// SWIZZLE_128B) stages A and W tiles in shared memory, one elected thread issues tcgen05.mma
+// (cta_group::1, kind::f16, M=128 x N=128 x K=16) with fp32 accumulators in TMEM, four epilogue warps
+// read them back with tcgen05.ld and apply the fused epilogue (bias / GELU / residual / GeGLU /
+// fp32 out) with the same rounding points as the SIMT reference kernel (gemm_simt.cu).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0  TMA producer      smem ring of NSTAGES x {A 128x64, W 128x64 [, W_up 128x64]}
+//   warp 1  MMA issuer        4 x tcgen05.mma per stage, tcgen05.commit frees the stage
+//   warp 2  TMEM allocator    512 columns = 2 accumulator stages x (1 or 2) x 128 columns
+//   warps 4-7 epilogue        TMEM -> registers -> global, overlapped with the next tile's MMAs
+// Used by the prefill / cache-off recompute / SigLIP / projector / lm_head(all positions) GEMMs of
+// the reference (every nn.Linear of SURVEY.md §2.3 with more than a handful of rows).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace pg {
-bool gemm_tc_supported(int, int, int, int, int, int, int, int, int) { return false; }
-int gemm_tc(void*, const void*, const void*, const void*, const void*, int, int, int, int, int, int, int, int,
-            int, int, int, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int TILE_BYTES = BM * BK * 2;  // 16 KB, also BN*BK*2
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
+// [0,14), LBO=1 in [16,30), SBO = 8 rows x 128 B = 1024 B (>>4 = 64) in [32,46), version 1 in [46,48),
+// layout type 2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A/B format [7,10),[10,13)
+// (0 f16, 1 bf16), both K-major, N>>3 in [17,23), M>>4 in [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int m, int n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Params {
+  void* C;
+  const void* bias;
+  const void* R;
+  int M, N, K, ldc, ldr, res_mod, out_f32;
+};
+
+template <typename T, int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, Params p) {
+  constexpr bool DUAL = (EPI == PG_EPI_GEGLU);
+  constexpr int NB_TILES = DUAL ? 2 : 1;              // W tiles per stage
+  constexpr int NSTAGES = DUAL ? 4 : 6;
+  constexpr int STAGE_BYTES = (1 + NB_TILES) * TILE_BYTES;
+  constexpr int ACC_COLS = NB_TILES * BN;             // TMEM columns per accumulator stage
+  constexpr uint32_t IDESC = umma_idesc(std::is_same<T, bf16>::value ? 1 : 0, BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
+  const uint32_t bars = smem_base + NSTAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (NSTAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * NSTAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile / m_tiles, m_blk = tile % m_tiles;  // neighbours share the W tile (L2 reuse)
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(sa + TILE_BYTES, &map_w, full_bar(stage), kb * BK, n_blk * BN);
+          if (DUAL) tma_load_2d(sa + 2 * TILE_BYTES, &map_w, full_bar(stage), kb * BK, p.N + n_blk * BN);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = umma_desc(sa + k * UMMA_K * 2);
+            const uint32_t accumulate = (kb > 0 || k > 0) ? 1u : 0u;
+            umma(d_tmem, ad, umma_desc(sa + TILE_BYTES + k * UMMA_K * 2), IDESC, accumulate);
+            if (DUAL) umma(d_tmem + BN, ad, umma_desc(sa + 2 * TILE_BYTES + k * UMMA_K * 2), IDESC, accumulate);
+          }
+          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    T* Ct = reinterpret_cast<T*>(p.C);
+    float* Cf = reinterpret_cast<float*>(p.C);
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const T* R = reinterpret_cast<const T*>(p.R);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile / m_tiles, m_blk = tile % m_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32], u[DUAL ? 32 : 1];
+        tmem_ld32(t_row + c * 32, v);
+        if (DUAL) tmem_ld32(t_row + BN + c * 32, u);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (m < p.M && n0 < p.N) {
+          const int rm = p.res_mod > 0 ? (m % p.res_mod) : m;
+#pragma unroll
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            if (n0 + j0 >= p.N) break;  // N is a multiple of 8 (checked on the host)
+            float o[8];
+            float bb[8], rr[8];
+            if (EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES)
+              unpack<T>(ldg_cached(bias + n0 + j0), bb);
+            if (EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES) unpack<T>(ldg_cached(R + (size_t)rm * p.ldr + n0 + j0), rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = v[j0 + j];
+              if (EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES) x += bb[j];
+              x = rnd<T>(x);
+              if (EPI == PG_EPI_BIAS_GELU) x = rnd<T>(gelu_tanh(x));
+              if (EPI == PG_EPI_GEGLU) x = rnd<T>(rnd<T>(gelu_tanh(x)) * rnd<T>(u[DUAL ? j0 + j : 0]));
+              if (EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES) x = rnd<T>(x + rr[j]);
+              o[j] = x;
+            }
+            if (p.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(Cf + (size_t)m * p.ldc + n0 + j0);
+              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+              *reinterpret_cast<uint4*>(Ct + (size_t)m * p.ldc + n0 + j0) = pack<T>(o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D row-major [rows, K] tensor, box = 64 (K) x 128 rows, 128-byte swizzle, zero fill out of bounds.
+static bool make_map(CUtensorMap* map, const void* base, int rows, int K, int ld, bool is_bf16) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <typename T, int EPI>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
+  constexpr bool DUAL = (EPI == PG_EPI_GEGLU);
+  constexpr int NSTAGES = DUAL ? 4 : 6;
+  constexpr int STAGE_BYTES = (DUAL ? 3 : 2) * TILE_BYTES;
+  const size_t smem = 1024 + (size_t)NSTAGES * STAGE_BYTES + 8 * (2 * NSTAGES + 4) + 16;
+  auto kern = gemm_tc_kernel<T, EPI>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("gemm_tc: cannot reserve %zu B of shared memory", smem);
+    cudaGetLastError();
+    return PG_ERR_CUDA;
+  }
+  const int tiles = cdiv(p.M, BM) * cdiv(p.N, BN);
+  const int grid = tiles < 148 ? tiles : 148;
+  kern<<<grid, THREADS, smem, st>>>(ma, mw, p);
+  return check_launch("gemm_tcgen05");
+}
+
+}  // namespace tc
+
+bool gemm_tc_supported(int M, int N, int K, int lda, int ldw, int ldc, int epi, int out_f32, int dtype) {
+  static const int enabled = env_int("PG_TCGEN05", 1);
+  static const int min_m = env_int("PG_TCGEN05_MIN_M", 16);
+  if (!enabled || (dtype != PG_BF16 && dtype != PG_F16)) return false;
+  if (M < min_m || N % 8 || K % 8 || lda % 8 || ldw % 8 || ldc % (out_f32 ? 4 : 8)) return false;
+  if (epi < PG_EPI_NONE || epi > PG_EPI_GEGLU) return false;
+  return tc::encode_fn() != nullptr;
+}
+
+int gemm_tc(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
+            int ldw, int ldc, int ldr, int res_mod, int epi, int out_f32, int dtype, cudaStream_t st) {
+  PG_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)C % 16) == 0,
+             "gemm_tc: operands must be 16-byte aligned");
+  PG_REQUIRE(!R || (((uintptr_t)R % 16) == 0 && ldr % 8 == 0), "gemm_tc: residual must be 16-byte aligned rows");
+  PG_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_tc: bias must be 16-byte aligned");
+  const bool bf = dtype == PG_BF16;
+  CUtensorMap ma, mw;
+  const int w_rows = (epi == PG_EPI_GEGLU) ? 2 * N : N;
+  PG_REQUIRE(tc::make_map(&ma, A, M, K, lda, bf) && tc::make_map(&mw, W, w_rows, K, ldw, bf),
+             "gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", M, N, K, lda, ldw);
+  tc::Params p = {C, bias, R, M, N, K, ldc, ldr, res_mod, out_f32};
+#define PG_TC(E) \
+  return bf ? tc::launch<bf16, E>(ma, mw, p, st) : tc::launch<f16, E>(ma, mw, p, st)
+  switch (epi) {
+    case PG_EPI_NONE: PG_TC(PG_EPI_NONE);
+    case PG_EPI_BIAS: PG_TC(PG_EPI_BIAS);
+    case PG_EPI_BIAS_GELU: PG_TC(PG_EPI_BIAS_GELU);
+    case PG_EPI_BIAS_RES: PG_TC(PG_EPI_BIAS_RES);
+    case PG_EPI_RES: PG_TC(PG_EPI_RES);
+    case PG_EPI_GEGLU: PG_TC(PG_EPI_GEGLU);
+  }
+#undef PG_TC
+  set_error("gemm_tc: bad epilogue %d", epi);
   return PG_ERR_INVALID;
 }
+
 }  // namespace pg

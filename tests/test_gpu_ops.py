@@ -341,3 +341,47 @@ def test_top_p_nucleus_matches_reference_rule(V):
     # the peaked row is dominated by its few boosted tokens
     assert set(draws[:, 2].tolist()) <= set(torch.nonzero(dist[2]).flatten().tolist())
     assert len(set(draws[:, 0].tolist())) > 10  # and it really samples
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (260, 2560, 2048), (256, 1152, 4304), (70, 272, 144),
+                                   (33, 4304, 1152), (512, 1152, 592), (1000, 2048, 2048), (16, 8, 8)])
+@pytest.mark.parametrize("epi", ["none", "bias", "bias_gelu", "bias_res", "res", "geglu", "f32", "posemb"])
+def test_gemm_tcgen05(dtype, M, N, K, epi):
+    """The tcgen05/TMEM/TMA GEMM (impl=2) against torch on CPU in the same dtype and against the SIMT
+    kernel (same rounding points, different accumulation order)."""
+    a = gen(M, K, dtype=dtype)
+    s = 1.0 / math.sqrt(K)
+    w, w2 = gen(N, K, seed=1, scale=s, dtype=dtype), gen(N, K, seed=2, scale=s, dtype=dtype)
+    bias = gen(N, seed=3, scale=0.1, dtype=dtype)
+    res_mod = 16 if epi == "posemb" else 0
+    res = gen(16 if epi == "posemb" else M, N, seed=4, dtype=dtype)
+    code = dict(none=cabi.EPI_NONE, bias=cabi.EPI_BIAS, bias_gelu=cabi.EPI_BIAS_GELU, bias_res=cabi.EPI_BIAS_RES,
+                res=cabi.EPI_RES, geglu=cabi.EPI_GEGLU, f32=cabi.EPI_NONE, posemb=cabi.EPI_BIAS_RES)[epi]
+    if epi == "none":
+        want = F.linear(a, w)
+    elif epi == "bias":
+        want = F.linear(a, w, bias)
+    elif epi == "bias_gelu":
+        want = F.gelu(F.linear(a, w, bias), approximate="tanh")
+    elif epi == "bias_res":
+        want = F.linear(a, w, bias) + res
+    elif epi == "res":
+        want = F.linear(a, w) + res
+    elif epi == "geglu":
+        want = F.gelu(F.linear(a, w), approximate="tanh") * F.linear(a, w2)
+    elif epi == "posemb":
+        want = F.linear(a, w, bias) + res[torch.arange(M) % 16]
+    else:
+        want = F.linear(a, w).float()
+    wd = dev(torch.cat([w, w2], 0)) if epi == "geglu" else dev(w)
+    ad, bd, rd = dev(a), dev(bias), dev(res)
+    outs = []
+    for impl in (2, 1):
+        out = torch.full((M, N), float("nan"), dtype=torch.float32 if epi == "f32" else dtype, device="cuda")
+        cabi.check(cabi.lib().pg_gemm(out.data_ptr(), ad.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), M, N, K,
+                                      K, K, N, N, res_mod, code, 1 if epi == "f32" else 0, impl,
+                                      cabi.DTYPE_CODE[dtype], st()))
+        outs.append(out)
+    close(outs[0], want, dtype)
+    close(outs[0], outs[1].cpu(), dtype)
