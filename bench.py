@@ -125,6 +125,20 @@ def barrier(world: int):
     torch.cuda.synchronize()
 
 
+def build_weights_gpu(cfg, dtype):
+    """Same-seed random weights generated on each rank's GPU (timing runs with N > 1: identical on every
+    rank, no 12 GB CPU checkpoint per process)."""
+    from pg_b200 import synth
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    sd = {}
+    for key, shape, kind in synth.state_dict_spec(cfg):
+        t = torch.randn(shape, generator=g, device="cuda", dtype=torch.float32) * synth._STD[kind]
+        if kind == "ln_w":
+            t += 1
+        sd[key] = t.to(dtype)
+    return sd
+
+
 def build_weights_cpu(cfg):
     from pg_b200 import synth
     t0 = time.time()
@@ -132,9 +146,10 @@ def build_weights_cpu(cfg):
     return sd, time.time() - t0
 
 
-def build_model(cfg, sd_cpu, dtype):
+def build_model(cfg, sd_cpu, dtype, tp=None):
     import modeling_gemma as MG
-    model = MG.PaliGemmaForConditionalGeneration(MG.PaliGemmaConfig(**cfg), init_weights=False)
+    opts = {} if tp is None else {"tp": tp}
+    model = MG.PaliGemmaForConditionalGeneration(MG.PaliGemmaConfig(**cfg), init_weights=False, **opts)
     for key, t in sd_cpu.items():
         if key.endswith("lm_head.weight"):
             continue
@@ -200,13 +215,14 @@ def time_dominant_kernel(eng, reps: int = 3):
     from pg_b200 import _cabi as cabi
     d = eng.dims
     x = torch.randn(1, d.D, device="cuda").to(eng.dtype)
-    out = torch.empty(1, d.F, dtype=eng.dtype, device="cuda")
+    F_l = eng.F_l
+    out = torch.empty(1, F_l, dtype=eng.dtype, device="cuda")
     L, st = cabi.lib(), cabi.stream()
 
     def sweep():
         for w in eng.t_layers:
             cabi.check(L.pg_decode_gateup(out.data_ptr(), x.data_ptr(), w["ln2"].data_ptr(), w["gu"].data_ptr(), 1,
-                                          d.D, d.F, d.eps, eng.dt, st))
+                                          d.D, F_l, d.eps, eng.dt, st))
     sweep()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -217,7 +233,7 @@ def time_dominant_kernel(eng, reps: int = 3):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (reps * len(eng.t_layers))
     esize = torch.tensor([], dtype=eng.dtype).element_size()
-    bytes_per_launch = esize * (2 * d.F * d.D + 2 * d.D) + esize * d.F
+    bytes_per_launch = esize * (2 * F_l * d.D + 2 * d.D) + esize * F_l
     return ms, bytes_per_launch
 
 
@@ -227,8 +243,19 @@ def run_ours(args, rank, world, local):
     cfg = synth.CONFIGS[MODEL]
     dtype = torch.bfloat16
     B, K, W = args.batch, args.steps, args.warmup
-    sd_cpu, t_weights = build_weights_cpu(cfg)
-    model = build_model(cfg, sd_cpu, dtype)
+    from pg_b200.dist import TP
+    use_tp = world > 1 and args.parallel == "tp"
+    tp = TP(rank, world, None) if use_tp else None
+    t0 = time.time()
+    if world > 1:
+        sd_cpu, t_weights = build_weights_gpu(cfg, dtype), 0.0
+    else:
+        sd_cpu, t_weights = build_weights_cpu(cfg)
+    model = build_model(cfg, sd_cpu, dtype, tp)
+    if world > 1:
+        sd_cpu = None
+        t_weights = time.time() - t0
+    streams = 1 if use_tp else world   # independent token streams across the job
     eng = model._engine_ready()
     d = eng.dims
     ids = synth.synth_prompt_ids(cfg, batch=B)
@@ -264,7 +291,7 @@ def run_ours(args, rank, world, local):
     total_ms = evs[0].elapsed_time(evs[-1])
     per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
     total_ms = max_over_ranks(total_ms, world)
-    value = world * B * K / (total_ms / 1e3)
+    value = streams * B * K / (total_ms / 1e3)
     ctx_mid = N + W + K // 2
     kv.release()
 
@@ -294,7 +321,7 @@ def run_ours(args, rank, world, local):
             torch.cuda.synchronize()
             e2e_ms = (time.perf_counter() - t0) * 1e3
         e2e_ms = max_over_ranks(e2e_ms, world)
-        e2e = {"value": world * B * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * B,
+        e2e = {"value": streams * B * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * B,
                "d2h_bytes_per_step": 8 * B, "ms_per_step": e2e_ms / K,
                "api": "PaliGemmaForConditionalGeneration.forward(input_ids, pixel_values, attention_mask, kv_cache) per token"}
         kvc._paged.release()
@@ -341,11 +368,13 @@ def run_ours(args, rank, world, local):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if use_tp else "weak",
+        "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{MODEL} random-init, batch {B}/GPU, 1 synthetic 224x224 image + 'caption en' prompt (N={N}), "
                                f"greedy cached decode (BASELINE.json configs[0], bf16)",
-                   "kv_cache": True, "context_at_mid_run": ctx_mid, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                   "kv_cache": True, "context_at_mid_run": ctx_mid, "parallelism": (f"tp{world} (heads / MLP / vocab sharded, NCCL all-reduce x36 + all-gather per step)" if use_tp
+                                   else (f"replicas x{world}" if world > 1 else "single GPU")),
                    "l2": "inputs (5.0 GB weight stream per step) larger than the 126 MB L2; no flush needed"},
         "p50_ms_per_token": statistics.median(per_step),
         "e2e": e2e,
@@ -372,6 +401,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--kv-off-steps", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--parallel", default="tp", choices=["tp", "replicas"],
+                    help="N > 1: tensor-parallel single stream (north star) or independent replicas")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -379,12 +410,12 @@ def main():
         run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
         return
     rank, world, local = dist_setup(args.gpus)
-    try:
-        run_ours(args, rank, world, local)
-    finally:
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
+    run_ours(args, rank, world, local)
+    if world > 1:
+        # graphs that captured NCCL kernels are still alive; communicator teardown can block under them
+        sys.stdout.flush()
+        barrier(world)
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -23,6 +23,7 @@ import torch
 
 from . import _cabi as cabi
 from ._cabi import ptr
+from .dist import TP, check_divisible, combine_argmax_keys, shard_rows, shard_text_layer
 
 
 def _get(obj, name, default=None):
@@ -118,9 +119,14 @@ class PaliGemmaEngine:
 
     def __init__(self, config, weights: Mapping[str, torch.Tensor], *, device=None, dtype=None,
                  page_size: int = 64, kv_pool_tokens: int = 65536, gemm_impl: int = 0,
-                 adopt=None):
+                 adopt=None, tp=None):
         cabi.lib()  # fail now if the CUDA library is missing
         self.dims = d = Dims.from_config(config)
+        self.tp = tp if tp is not None else TP()
+        if self.tp.active:
+            check_divisible(d, self.tp.size)
+            adopt = None  # shards do not have the parameters' shapes
+        self.nq_l, self.F_l, self.V_l = d.nq // self.tp.size, d.F // self.tp.size, d.V // self.tp.size
         emb = weights["language_model.model.embed_tokens.weight"]
         self.device = torch.device(device) if device is not None else emb.device
         if self.device.type != "cuda":
@@ -184,12 +190,21 @@ class PaliGemmaEngine:
         head = weights.get("language_model.lm_head.weight")
         self.lm_head = self.emb if (head is None or head.data_ptr() == weights[lm + "embed_tokens.weight"].data_ptr()) \
             else W("language_model.lm_head.weight")
+        if self.tp.active:
+            self.lm_head = shard_rows(self.lm_head, self.tp.rank, self.tp.size)
         self.t_layers = []
         for i in range(d.L):
             Lk = f"{lm}layers.{i}."
             names = ("q_proj", "k_proj", "v_proj")
-            qkv = torch.cat([W(Lk + f"self_attn.{n}.weight") for n in names], 0)
-            gu = torch.cat([W(Lk + "mlp.gate_proj.weight"), W(Lk + "mlp.up_proj.weight")], 0)
+            if self.tp.active:
+                qkv, o, gu, down = shard_text_layer(
+                    W(Lk + "self_attn.q_proj.weight"), W(Lk + "self_attn.k_proj.weight"), W(Lk + "self_attn.v_proj.weight"),
+                    W(Lk + "self_attn.o_proj.weight"), W(Lk + "mlp.gate_proj.weight"), W(Lk + "mlp.up_proj.weight"),
+                    W(Lk + "mlp.down_proj.weight"), self.tp.rank, self.tp.size)
+            else:
+                qkv = torch.cat([W(Lk + f"self_attn.{n}.weight") for n in names], 0)
+                gu = torch.cat([W(Lk + "mlp.gate_proj.weight"), W(Lk + "mlp.up_proj.weight")], 0)
+                o, down = W(Lk + "self_attn.o_proj.weight"), W(Lk + "mlp.down_proj.weight")
             if adopt:
                 off = 0
                 for n in names:
@@ -199,8 +214,8 @@ class PaliGemmaEngine:
                 adopt(Lk + "mlp.gate_proj.weight", gu[:d.F])
                 adopt(Lk + "mlp.up_proj.weight", gu[d.F:])
             self.t_layers.append(dict(
-                ln1=W(Lk + "input_layernorm.weight"), qkv=qkv, o=W(Lk + "self_attn.o_proj.weight"),
-                ln2=W(Lk + "post_attention_layernorm.weight"), gu=gu, down=W(Lk + "mlp.down_proj.weight")))
+                ln1=W(Lk + "input_layernorm.weight"), qkv=qkv, o=o,
+                ln2=W(Lk + "post_attention_layernorm.weight"), gu=gu, down=down))
         self.final_norm = W(lm + "norm.weight")
         # RoPE frequencies (modeling_gemma.py:151): the buffer is rounded by model.to(dtype)
         f = 1.0 / (d.theta ** (torch.arange(0, d.hd, 2, dtype=torch.int64).float() / d.hd))
@@ -212,8 +227,8 @@ class PaliGemmaEngine:
     def weight_bytes_per_decode_step(self) -> int:
         """Algorithmic HBM bytes one decode step must read from the weights."""
         d, e = self.dims, torch.tensor([], dtype=self.dtype).element_size()
-        per_layer = ((d.nq + 2 * d.nkv) * d.hd * d.D + d.D * d.nq * d.hd + 3 * d.F * d.D + 2 * d.D)
-        return e * (d.L * per_layer + d.V * d.D + d.D)
+        per_layer = ((self.nq_l + 2 * d.nkv) * d.hd * d.D + d.D * self.nq_l * d.hd + 3 * self.F_l * d.D + 2 * d.D)
+        return e * (d.L * per_layer + self.V_l * d.D + d.D)
 
     # ------------------------------------------------------------------ KV pages
     def _alloc_pages(self, n: int) -> List[int]:
@@ -322,33 +337,45 @@ class PaliGemmaEngine:
             cabi.check(L.pg_embed_merge(ptr(x), ptr(ids), ptr(self.emb), ptr(img), T, d.D, d.V,
                                         d.image_token_index, d.pad_token_id, 0 if img is None else img.shape[0],
                                         self.img_div, self.normalizer, ptr(self.err_flag), self.dt, st), "embed_merge")
-            nqkv = (d.nq + 2 * d.nkv) * d.hd
-            n, qkv, qo = self._new(T, d.D), self._new(T, nqkv), self._new(T, d.nq * d.hd)
-            att, x2, g = self._new(T, d.nq * d.hd), self._new(T, d.D), self._new(T, d.F)
+            nq, tp = self.nq_l, self.tp
+            res_epi = cabi.EPI_RES if tp.rank == 0 else cabi.EPI_NONE   # the residual enters the sum once
+            nqkv = (nq + 2 * d.nkv) * d.hd
+            n, qkv, qo = self._new(T, d.D), self._new(T, nqkv), self._new(T, nq * d.hd)
+            att, x2, g = self._new(T, nq * d.hd), self._new(T, d.D), self._new(T, self.F_l)
             scale_div = float(math.sqrt(d.hd))
             for li, w in enumerate(self.t_layers):
                 cabi.check(L.pg_rmsnorm(ptr(n), ptr(x), ptr(w["ln1"]), T, d.D, d.eps, self.dt, st), "rmsnorm")
                 self._gemm(qkv, n, w["qkv"])
                 cabi.check(L.pg_rope_append(ptr(qo), ptr(qkv), ptr(self.inv_freq), ptr(pos), ptr(self.k_pool[li]),
                                             ptr(self.v_pool[li]), ptr(kv.page_table), kv.max_pages, self.page_size,
-                                            ptr(kv.kv_len), B, q, d.nq, d.nkv, d.hd, d.max_pos, self.dt, st), "rope_append")
-                cabi.check(L.pg_attention(ptr(att), d.nq * d.hd, ptr(qo), d.nq * d.hd, ptr(self.k_pool[li]),
+                                            ptr(kv.kv_len), B, q, nq, d.nkv, d.hd, d.max_pos, self.dt, st), "rope_append")
+                cabi.check(L.pg_attention(ptr(att), nq * d.hd, ptr(qo), nq * d.hd, ptr(self.k_pool[li]),
                                           ptr(self.v_pool[li]), 0, 0, ptr(kv.page_table), kv.max_pages, self.page_size,
-                                          ptr(kv.kv_len), 0, q, B, q, d.nq, d.nkv, d.hd, scale_div, 1, self.dt, st),
+                                          ptr(kv.kv_len), 0, q, B, q, nq, d.nkv, d.hd, scale_div, 1, self.dt, st),
                            "attention")
-                self._gemm(x2, att, w["o"], None, x, cabi.EPI_RES)
+                self._gemm(x2, att, w["o"], None, x if tp.rank == 0 else None, res_epi)
+                tp.all_reduce(x2)
                 cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), T, d.D, d.eps, self.dt, st), "rmsnorm")
                 self._gemm(g, n, w["gu"], None, None, cabi.EPI_GEGLU)
-                self._gemm(x, g, w["down"], None, x2, cabi.EPI_RES)
+                self._gemm(x, g, w["down"], None, x2 if tp.rank == 0 else None, res_epi)
+                tp.all_reduce(x)
             kv.kv_len.add_(q)
             kv.length = cached + q
             if logits == "last":
                 x = x.view(B, q, d.D)[:, -1].contiguous()
             rows = x.shape[0]
-            h = self._new(rows, d.D)
-            cabi.check(L.pg_rmsnorm(ptr(h), ptr(x), ptr(self.final_norm), rows, d.D, d.eps, self.dt, st), "final norm")
-            out = self._new(rows, d.V, dtype=torch.float32)
-            self._gemm(out, h, self.lm_head, out_f32=True)
+            out = self._new(rows, self.V_l, dtype=torch.float32)
+            if rows <= cabi.MAX_DECODE_BATCH:
+                # a handful of rows: the weight-streaming lm_head kernel (final norm fused) beats a GEMM tile
+                cabi.check(L.pg_decode_lmhead(ptr(out), ptr(x), ptr(self.final_norm), ptr(self.lm_head), rows, d.D,
+                                              self.V_l, d.eps, None, self.dt, st), "lm_head")
+            else:
+                h = self._new(rows, d.D)
+                cabi.check(L.pg_rmsnorm(ptr(h), ptr(x), ptr(self.final_norm), rows, d.D, d.eps, self.dt, st), "final norm")
+                self._gemm(out, h, self.lm_head, out_f32=True)
+            if tp.active:  # vocab shards -> full rows
+                gathered = tp.all_gather(self._new(tp.size, rows, self.V_l, dtype=torch.float32), out)
+                out = gathered.permute(1, 0, 2).reshape(rows, d.V)
             return out.view(B, -1, d.V)
         finally:
             if temp:
@@ -390,12 +417,16 @@ class DecodeState:
         self.sampled = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.x = eng._new(batch, d.D)
         self.x2 = eng._new(batch, d.D)
-        self.q = eng._new(batch, d.nq * d.hd)
-        self.att = eng._new(batch, d.nq * d.hd)
-        self.g = eng._new(batch, d.F)
-        nws = cabi.lib().pg_decode_attention_ws_floats(batch, d.nq, d.hd, eng.max_splits)
-        self.ws = torch.zeros(int(nws), dtype=torch.float32, device=dev)
+        self.q = eng._new(batch, eng.nq_l * d.hd)
+        self.att = eng._new(batch, eng.nq_l * d.hd)
+        self.g = eng._new(batch, eng.F_l)
+        self.ws = torch.zeros(1, dtype=torch.float32, device=dev)       # (unused by the cluster kernel)
         self.counters = torch.zeros(batch * d.nkv, dtype=torch.int32, device=dev)
+        tp = eng.tp
+        self.local_logits = self.logits if not tp.active else torch.zeros((batch, eng.V_l), dtype=torch.float32, device=dev)
+        self.gather_logits = torch.zeros((tp.size, batch, eng.V_l), dtype=torch.float32, device=dev) if tp.active else None
+        self.gather_keys = torch.zeros((tp.size, batch), dtype=torch.int64, device=dev) if tp.active else None
+        self.want_full_logits = True   # TP: gather the vocab shards every step (API parity / sampling)
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.pf_cap_mb = float(os.environ.get("PG_PF_MB", "0"))   # L2 prefetch distance per launch (0 = off)
         self.kv: Optional[PagedKV] = None
@@ -422,6 +453,8 @@ class DecodeState:
         scale_div = float(math.sqrt(d.hd))
         MB = cabi.MAX_DECODE_BATCH
         x, x2 = self.x, self.x2
+        tp, nq, F_l = eng.tp, eng.nq_l, eng.F_l
+        zero_res = None
         for li, w in enumerate(eng.t_layers):
             kp, vp = eng.k_pool[li], eng.v_pool[li]
             nxt = eng.t_layers[li + 1]["qkv"] if li + 1 < len(eng.t_layers) else eng.lm_head
@@ -430,32 +463,45 @@ class DecodeState:
                 nb = min(MB, B - b0)
                 cabi.check(L.pg_decode_qkv(ptr(self.q[b0:]), ptr(x[b0:]), ptr(w["ln1"]), ptr(w["qkv"]), ptr(eng.inv_freq),
                                            ptr(self.pos[b0:]), ptr(kp), ptr(vp), ptr(kv.page_table[b0:]), kv.max_pages,
-                                           eng.page_size, ptr(kv.kv_len[b0:]), nb, d.D, d.nq, d.nkv, d.hd, d.eps,
+                                           eng.page_size, ptr(kv.kv_len[b0:]), nb, d.D, nq, d.nkv, d.hd, d.eps,
                                            d.max_pos, dt, st), "decode_qkv")
             self._pf(w["gu"])                                  # attention pulls the head of gate/up
             cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
-                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, d.nq, d.nkv, d.hd,
+                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, nq, d.nkv, d.hd,
                                              scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
                        "decode_attention")
             for b0 in range(0, B, MB):
                 nb = min(MB, B - b0)
                 if b0 == 0:
                     self._pf(w["gu"], start_mb=cap)            # o_proj pulls the next slice of gate/up
-                cabi.check(L.pg_gemv_res(ptr(x2[b0:]), ptr(self.att[b0:]), ptr(w["o"]), ptr(x[b0:]), nb, d.D,
-                                         d.nq * d.hd, dt, st), "o_proj")
+                # tensor parallel: only rank 0 adds the residual, so it enters the all-reduced sum once
+                cabi.check(L.pg_gemv_res(ptr(x2[b0:]), ptr(self.att[b0:]), ptr(w["o"]),
+                                         ptr(x[b0:]) if tp.rank == 0 else None, nb, d.D, nq * d.hd, dt, st), "o_proj")
+            tp.all_reduce(x2)
+            for b0 in range(0, B, MB):
+                nb = min(MB, B - b0)
                 if b0 == 0:
                     self._pf(w["down"], cap_mb=1.5 * cap)      # gate/up pulls the head of down_proj
                 cabi.check(L.pg_decode_gateup(ptr(self.g[b0:]), ptr(x2[b0:]), ptr(w["ln2"]), ptr(w["gu"]), nb, d.D,
-                                              d.F, d.eps, dt, st), "gateup")
+                                              F_l, d.eps, dt, st), "gateup")
                 if b0 == 0:
                     self._pf(nxt, cap_mb=1.5 * cap)            # down_proj pulls the next layer's qkv / lm_head
-                cabi.check(L.pg_gemv_res(ptr(x[b0:]), ptr(self.g[b0:]), ptr(w["down"]), ptr(x2[b0:]), nb, d.D, d.F,
-                                         dt, st), "down_proj")
+                cabi.check(L.pg_gemv_res(ptr(x[b0:]), ptr(self.g[b0:]), ptr(w["down"]),
+                                         ptr(x2[b0:]) if tp.rank == 0 else None, nb, d.D, F_l, dt, st), "down_proj")
+            tp.all_reduce(x)
         self._pf(eng.t_layers[0]["qkv"])                       # lm_head pulls layer 0 for the next step
         for b0 in range(0, B, MB):
             nb = min(MB, B - b0)
-            cabi.check(L.pg_decode_lmhead(ptr(self.logits[b0:]), ptr(x[b0:]), ptr(eng.final_norm), ptr(eng.lm_head),
-                                          nb, d.D, d.V, d.eps, ptr(self.keys[b0:]), dt, st), "lm_head")
+            cabi.check(L.pg_decode_lmhead(ptr(self.local_logits[b0:]), ptr(x[b0:]), ptr(eng.final_norm), ptr(eng.lm_head),
+                                          nb, d.D, eng.V_l, d.eps, ptr(self.keys[b0:]), dt, st), "lm_head")
+        tp_token = None
+        if tp.active:
+            # vocab-sharded lm_head: gather the per-rank (max, index) pairs; full logits only on request
+            tp.all_gather(self.gather_keys, self.keys)
+            tp_token = combine_argmax_keys(self.gather_keys, eng.V_l)
+            if self.want_full_logits or sample is not None:
+                tp.all_gather(self.gather_logits, self.local_logits)
+                self.logits.view(B, tp.size, eng.V_l).copy_(self.gather_logits.permute(1, 0, 2))
         sampled = None
         if sample is not None:
             temperature, top_p, seed = sample
@@ -464,6 +510,9 @@ class DecodeState:
             cabi.check(L.pg_top_p_sample(ptr(self.sampled), ptr(self.logits), ptr(self.probs), B, d.V,
                                          float(temperature), float(top_p), int(seed), ptr(self.step), None, st),
                        "top_p")
+            sampled = self.sampled
+        elif tp_token is not None:
+            self.sampled.copy_(tp_token)
             sampled = self.sampled
         if advance:
             cabi.check(L.pg_step_advance(ptr(self.ids), ptr(self.history), self.max_hist, ptr(self.step),

@@ -284,3 +284,16 @@ def test_full_size_bf16_logits(golden_dir):
     assert rms(err) <= 2.5 * ref_noise
     # the token we would pick is one the reference also rates within the bf16 noise of its own best
     assert float(want.max() - want[0, int(lg.argmax())]) <= 4 * ref_noise
+
+
+def test_tensor_parallel_two_gpus():
+    """TP=2 over NCCL reproduces the reference's greedy tokens (needs 2 visible GPUs)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "tests", "tp_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert "TP_CHECK_PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
