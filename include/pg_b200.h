@@ -94,6 +94,18 @@ int pg_attention(void* out, int ld_out, const void* q, int ld_q, const void* k, 
                  int q_len, int n_heads, int n_kv_heads, int hd, float scale, int scale_mode,
                  int dtype, void* stream);
 
+/* The same attention on the tcgen05 tensor cores (16-bit dtypes; prefill, cache-off recompute, SigLIP):
+ * QK^T and PV as tcgen05.mma with TMEM accumulators, Q/K/V tiles by TMA, two-pass softmax (row max, then
+ * exp / PV) with one thread per query row.  q, k, v are row-major matrices (`*_rows` x `ld_*`); head h sits
+ * at columns *_col0 + h*hd_stride .. +hd, and a head row must be padded (with zeros) to a multiple of 64
+ * columns unless hd is 128 or 256.  Paged K/V needs page_size == key tile (128 for hd <= 128, 64 above).
+ * Output is packed: head h at column h*hd of [B*q_len, ld_out]. */
+int pg_attention_tc(void* out, int ld_out, const void* q, long long q_rows, int ld_q, int q_col0,
+                    const void* k, const void* v, long long kv_rows, int ld_kv, int k_col0, int v_col0,
+                    int hd_stride, long long kv_batch_rows, const int32_t* page_table, int pt_stride,
+                    int page_size, const int32_t* kv_len, int kv_len_const, int kv_len_add, int B, int q_len,
+                    int n_heads, int n_kv_heads, int hd, float scale, int scale_mode, int dtype, void* stream);
+
 /* ---- decode path (q_len == 1 per sequence), B <= PG_MAX_DECODE_BATCH per call ----------- */
 #define PG_MAX_DECODE_BATCH 8
 

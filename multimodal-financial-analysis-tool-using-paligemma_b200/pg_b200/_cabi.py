@@ -33,6 +33,8 @@ SIGNATURES = {
     "pg_rope_append": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "pg_attention": [_vp, _i, _vp, _i, _vp, _vp, _i, _ll, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
                      _f, _i, _i, _vp],
+    "pg_attention_tc": [_vp, _i, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _ll, _vp, _i, _i, _vp, _i, _i, _i,
+                        _i, _i, _i, _i, _f, _i, _i, _vp],
     "pg_set_next_prefetch": [_vp, _ll],
     "pg_decode_qkv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f,
                       _i, _i, _vp],

@@ -138,6 +138,15 @@ class PaliGemmaEngine:
         self.gemm_impl = gemm_impl
         self.page_size = page_size
         self._vec = 4 if self.dtype == torch.float32 else 8
+        # tcgen05 attention (16-bit dtypes): SigLIP heads padded to 128 columns; Gemma needs hd 256 and 64-token pages
+        tc_ok = self.dtype != torch.float32 and os.environ.get("PG_ATTN_TC", "1") != "0"
+        hdv = d.Hv // d.heads_v
+        self.vision_head_pad = 128
+        self.attn_tc_vision = tc_ok and hdv <= 128 and hdv % 8 == 0
+        self.attn_tc_text = tc_ok and d.hd == 256 and page_size == 64
+        if self.attn_tc_vision:
+            adopt_outer = adopt
+            adopt = (lambda k, v: None if ".vision_model." in k else adopt_outer(k, v)) if adopt_outer else None
         self._repack(weights, adopt)
         # paged KV pool: [L, pages, page_size, nkv*hd] for K and for V
         self.num_pages = max(8, (kv_pool_tokens + page_size - 1) // page_size)
@@ -176,6 +185,15 @@ class PaliGemmaEngine:
             if adopt:
                 for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
                     adopt(Lk + f"self_attn.{n}.weight", qkv_w[j * d.Hv:(j + 1) * d.Hv])
+            if self.attn_tc_vision:
+                # head rows padded 72 -> 128 with zero weights / zero bias: the tcgen05 attention kernel
+                # reads whole 64-column blocks, and zeros contribute nothing to QK^T or PV
+                hdv, hp, nh = d.Hv // d.heads_v, self.vision_head_pad, d.heads_v
+                wp_ = torch.zeros((3, nh, hp, d.Hv), dtype=self.dtype, device=self.device)
+                wp_[:, :, :hdv] = qkv_w.view(3, nh, hdv, d.Hv)
+                bp_ = torch.zeros((3, nh, hp), dtype=self.dtype, device=self.device)
+                bp_[:, :, :hdv] = qkv_b.view(3, nh, hdv)
+                qkv_w, qkv_b = wp_.view(3 * nh * hp, d.Hv), bp_.view(-1)
             self.v_layers.append(dict(
                 ln1_w=W(Lk + "layer_norm1.weight"), ln1_b=W(Lk + "layer_norm1.bias"),
                 qkv_w=qkv_w, qkv_b=qkv_b,
@@ -274,17 +292,24 @@ class PaliGemmaEngine:
         cabi.check(L.pg_im2col(ptr(col), ptr(px), B, d.C, d.S, d.S, d.p, self.k_patch, self.dt, st), "im2col")
         h = self._new(T, d.Hv)
         self._gemm(h, col, self.v_patch_w, self.v_patch_b, self.v_pos, cabi.EPI_BIAS_RES, res_mod=d.P)
-        ln, qkv, att = self._new(T, d.Hv), self._new(T, 3 * d.Hv), self._new(T, d.Hv)
-        h2, mid = self._new(T, d.Hv), self._new(T, d.Iv)
         hdv = d.Hv // d.heads_v
+        qkv_cols = 3 * d.heads_v * self.vision_head_pad if self.attn_tc_vision else 3 * d.Hv
+        ln, qkv, att = self._new(T, d.Hv), self._new(T, qkv_cols), self._new(T, d.Hv)
+        h2, mid = self._new(T, d.Hv), self._new(T, d.Iv)
         scale = float(hdv ** -0.5)
         for w in self.v_layers:
             cabi.check(L.pg_layernorm(ptr(ln), ptr(h), ptr(w["ln1_w"]), ptr(w["ln1_b"]), T, d.Hv, d.eps_v, self.dt, st), "ln1")
             self._gemm(qkv, ln, w["qkv_w"], w["qkv_b"], None, cabi.EPI_BIAS)
-            cabi.check(L.pg_attention(ptr(att), d.Hv, ptr(qkv), 3 * d.Hv, qkv[:, d.Hv:].data_ptr(),
-                                      qkv[:, 2 * d.Hv:].data_ptr(), 3 * d.Hv, d.P * 3 * d.Hv, None, 0, 0,
-                                      None, d.P, 0, B, d.P, d.heads_v, d.heads_v, hdv, scale, 0, self.dt, st),
-                       "siglip attention")
+            if self.attn_tc_vision:
+                hp = self.vision_head_pad
+                cabi.check(L.pg_attention_tc(ptr(att), d.Hv, ptr(qkv), T, qkv_cols, 0, ptr(qkv), ptr(qkv), T, qkv_cols,
+                                             d.heads_v * hp, 2 * d.heads_v * hp, hp, d.P, None, 0, 0, None, d.P, 0, B, d.P,
+                                             d.heads_v, d.heads_v, hdv, scale, 0, self.dt, st), "siglip attention (tcgen05)")
+            else:
+                cabi.check(L.pg_attention(ptr(att), d.Hv, ptr(qkv), 3 * d.Hv, qkv[:, d.Hv:].data_ptr(),
+                                          qkv[:, 2 * d.Hv:].data_ptr(), 3 * d.Hv, d.P * 3 * d.Hv, None, 0, 0,
+                                          None, d.P, 0, B, d.P, d.heads_v, d.heads_v, hdv, scale, 0, self.dt, st),
+                           "siglip attention")
             self._gemm(h2, att, w["o_w"], w["o_b"], h, cabi.EPI_BIAS_RES)
             cabi.check(L.pg_layernorm(ptr(ln), ptr(h2), ptr(w["ln2_w"]), ptr(w["ln2_b"]), T, d.Hv, d.eps_v, self.dt, st), "ln2")
             self._gemm(mid, ln, w["fc1_w"], w["fc1_b"], None, cabi.EPI_BIAS_GELU)
@@ -349,10 +374,17 @@ class PaliGemmaEngine:
                 cabi.check(L.pg_rope_append(ptr(qo), ptr(qkv), ptr(self.inv_freq), ptr(pos), ptr(self.k_pool[li]),
                                             ptr(self.v_pool[li]), ptr(kv.page_table), kv.max_pages, self.page_size,
                                             ptr(kv.kv_len), B, q, nq, d.nkv, d.hd, d.max_pos, self.dt, st), "rope_append")
-                cabi.check(L.pg_attention(ptr(att), nq * d.hd, ptr(qo), nq * d.hd, ptr(self.k_pool[li]),
-                                          ptr(self.v_pool[li]), 0, 0, ptr(kv.page_table), kv.max_pages, self.page_size,
-                                          ptr(kv.kv_len), 0, q, B, q, nq, d.nkv, d.hd, scale_div, 1, self.dt, st),
-                           "attention")
+                if self.attn_tc_text and q >= 16:
+                    cabi.check(L.pg_attention_tc(ptr(att), nq * d.hd, ptr(qo), T, nq * d.hd, 0, ptr(self.k_pool[li]),
+                                                 ptr(self.v_pool[li]), self.num_pages * self.page_size, d.nkv * d.hd, 0, 0,
+                                                 d.hd, 0, ptr(kv.page_table), kv.max_pages, self.page_size, ptr(kv.kv_len),
+                                                 0, q, B, q, nq, d.nkv, d.hd, scale_div, 1, self.dt, st),
+                               "attention (tcgen05)")
+                else:
+                    cabi.check(L.pg_attention(ptr(att), nq * d.hd, ptr(qo), nq * d.hd, ptr(self.k_pool[li]),
+                                              ptr(self.v_pool[li]), 0, 0, ptr(kv.page_table), kv.max_pages, self.page_size,
+                                              ptr(kv.kv_len), 0, q, B, q, nq, d.nkv, d.hd, scale_div, 1, self.dt, st),
+                               "attention")
                 self._gemm(x2, att, w["o"], None, x if tp.rank == 0 else None, res_epi)
                 tp.all_reduce(x2)
                 cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), T, d.D, d.eps, self.dt, st), "rmsnorm")

@@ -385,3 +385,41 @@ def test_gemm_tcgen05(dtype, M, N, K, epi):
         outs.append(out)
     close(outs[0], want, dtype)
     close(outs[0], outs[1].cpu(), dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,S,heads,hd", [(2, 256, 16, 72), (1, 16, 2, 72), (3, 64, 4, 72), (1, 300, 2, 128)])
+def test_attention_tc_siglip_padded_layout(dtype, B, S, heads, hd):
+    """tcgen05 attention on the SigLIP layout: fused [tokens, 3*heads*128] with each head padded to 128."""
+    hs = 128
+    q, k, v = (gen(B, heads, S, hd, seed=i, dtype=dtype) for i in (1, 2, 3))
+    w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
+    want = torch.matmul(F.softmax(w, dim=-1, dtype=torch.float32).to(dtype), v).transpose(1, 2).reshape(B * S, heads * hd)
+    fused = torch.zeros((B * S, 3, heads, hs), dtype=dtype)
+    for i, t in enumerate((q, k, v)):
+        fused[:, i, :, :hd] = t.transpose(1, 2).reshape(B * S, heads, hd)
+    fd = dev(fused.reshape(B * S, 3 * heads * hs))
+    out = torch.full((B * S, heads * hd), float("nan"), dtype=dtype, device="cuda")
+    ld = 3 * heads * hs
+    cabi.check(cabi.lib().pg_attention_tc(out.data_ptr(), heads * hd, fd.data_ptr(), B * S, ld, 0, fd.data_ptr(), fd.data_ptr(),
+                                          B * S, ld, heads * hs, 2 * heads * hs, hs, S, None, 0, 0, None, S, 0, B, S, heads,
+                                          heads, hd, float(hd ** -0.5), 0, cabi.DTYPE_CODE[dtype], st()))
+    close(out, want, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,q,T,nq", [(1, 260, 260, 8), (2, 37, 70, 8), (1, 130, 516, 4), (2, 16, 16, 2)])
+def test_attention_tc_gemma_paged(dtype, B, q, T, nq):
+    """tcgen05 attention over the paged KV pool (page == 64-key tile), MQA, head_dim 256."""
+    hd, nkv = 256, 1
+    qq = gen(B, nq, q, hd, seed=9, dtype=dtype)
+    k, v, kp, vp, pt, npg, page = _paged(B, T, nkv, hd, dtype, page=64)
+    want = _ref_attention(qq, k, v, math.sqrt(hd), dtype).transpose(1, 2).reshape(B * q, nq * hd)
+    qd = dev(qq.transpose(1, 2).reshape(B * q, nq * hd))
+    kvl = torch.full((B,), T - q, dtype=torch.int32, device="cuda")
+    out = torch.full((B * q, nq * hd), float("nan"), dtype=dtype, device="cuda")
+    rows = kp.shape[0] * page
+    cabi.check(cabi.lib().pg_attention_tc(out.data_ptr(), nq * hd, qd.data_ptr(), B * q, nq * hd, 0, kp.data_ptr(), vp.data_ptr(),
+                                          rows, nkv * hd, 0, 0, hd, 0, pt.data_ptr(), npg, page, kvl.data_ptr(), 0, q, B, q, nq,
+                                          nkv, hd, float(math.sqrt(hd)), 1, cabi.DTYPE_CODE[dtype], st()))
+    close(out, want, dtype)
