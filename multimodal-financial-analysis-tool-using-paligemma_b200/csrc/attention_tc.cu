@@ -11,6 +11,8 @@
 // Recomputing QK^T costs tensor-core time that is idle anyway and removes the online-softmax
 // correction of O.  Q, K, V tiles arrive by TMA; K/V may be contiguous or paged (page == key tile).
 // Head rows may be padded (hd_stride > hd): the SigLIP path pads 72 -> 128 with zero weights.
+#include <cmath>
+
 #include "tc_common.cuh"
 
 namespace pg {
@@ -36,15 +38,17 @@ struct AttnParams {
   int kv_len_const, kv_len_add;
   float scale;
   int scale_mode;                                // 0: s*scale, 1: s/scale
+  float scale_mul;                               // != 0: the scaling is exactly s*scale_mul (power-of-two divisor)
 };
 
 template <typename T, int HDP, int KT>  // HDP: padded head dim in shared memory (128 or 256); KT: keys per tile
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, HDP == 128 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, AttnParams p) {
   constexpr int KB = HDP / 64;                   // 64-column blocks of the head dim
   constexpr int Q_BYTES = AQ * HDP * 2, K_BYTES = KT * HDP * 2, V_BYTES = K_BYTES, P_BYTES = AQ * KT * 2;
   constexpr int S_COL = 0, O_COL = KT;           // TMEM columns
+  constexpr int TMEM_NEED = KT + HDP, TMEM_ALLOC = TMEM_NEED <= 256 ? 256 : 512;  // 256 lets two CTAs share an SM
   constexpr int FMT = std::is_same<T, bf16>::value ? 1 : 0;
 
   extern __shared__ uint8_t smem_raw[];
@@ -69,7 +73,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_ALLOC) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -136,7 +140,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = rnd<T>(s[j]);
-            x = rnd<T>(p.scale_mode ? x / p.scale : x * p.scale);
+            x = (p.scale_mul != 0.f) ? x * p.scale_mul : rnd<T>(p.scale_mode ? x / p.scale : x * p.scale);
             s[j] = (t * KT + c * 32 + j < T_len) ? x : -INFINITY;
           }
           if (pass == 0) {
@@ -190,7 +194,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC) : "memory");
   }
 }
 
@@ -230,7 +234,7 @@ extern "C" int pg_attention_tc(void* out, int ld_out, const void* q, long long q
              "attention_tc: rows must be 16-byte aligned");
   PG_REQUIRE(n_heads % n_kv_heads == 0, "attention_tc: bad head counts");
   const int hdp = hd <= 128 ? 128 : 256;
-  const int kt = hdp == 128 ? 128 : 64;
+  const int kt = 64;
   PG_REQUIRE(hd == hdp || hd_stride >= ((hd + 63) / 64) * 64 || n_heads == 1, "attention_tc: head rows must be padded to a multiple of 64 columns");
   PG_REQUIRE(!page_table || page_size == kt, "attention_tc: page size must equal the key tile (%d)", kt);
   const bool bf = dtype == PG_BF16;
@@ -239,8 +243,10 @@ extern "C" int pg_attention_tc(void* out, int ld_out, const void* q, long long q
                  tc::make_map_2d(&mv, v, kv_rows, ld_kv, ld_kv, kt, bf),
              "attention_tc: cuTensorMapEncodeTiled failed");
   tc::AttnParams p = {out, ld_out, hd, q_len, n_heads, n_heads / n_kv_heads, q_col0, k_col0, v_col0, hd_stride,
-                      kv_batch_rows, page_table, pt_stride, kv_len, kv_len_const, kv_len_add, scale, scale_mode};
+                      kv_batch_rows, page_table, pt_stride, kv_len, kv_len_const, kv_len_add, scale, scale_mode, 0.f};
+  int ex = 0;
+  if (scale_mode == 1 && frexpf(scale, &ex) == 0.5f) p.scale_mul = 1.0f / scale;  // x / 2^k == x * 2^-k exactly
   cudaStream_t st = (cudaStream_t)stream;
-  if (hdp == 128) return bf ? tc::launch_attn<bf16, 128, 128>(mq, mk, mv, p, B, st) : tc::launch_attn<f16, 128, 128>(mq, mk, mv, p, B, st);
+  if (hdp == 128) return bf ? tc::launch_attn<bf16, 128, 64>(mq, mk, mv, p, B, st) : tc::launch_attn<f16, 128, 64>(mq, mk, mv, p, B, st);
   return bf ? tc::launch_attn<bf16, 256, 64>(mq, mk, mv, p, B, st) : tc::launch_attn<f16, 256, 64>(mq, mk, mv, p, B, st);
 }

@@ -16,10 +16,10 @@
 namespace pg {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int THREADS = 256;
 constexpr int TMEM_COLS = 512;
-constexpr int TILE_BYTES = BM * BK * 2;  // 16 KB, also BN*BK*2
+constexpr int TILE_BYTES = BM * BK * 2;  // 16 KB (A tile; a W tile is BN*BK*2)
 
 struct Params {
   void* C;
@@ -28,13 +28,14 @@ struct Params {
   int M, N, K, ldc, ldr, res_mod, out_f32;
 };
 
-template <typename T, int EPI>
+template <typename T, int EPI, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, Params p) {
   constexpr bool DUAL = (EPI == PG_EPI_GEGLU);
   constexpr int NB_TILES = DUAL ? 2 : 1;              // W tiles per stage
-  constexpr int NSTAGES = DUAL ? 4 : 6;
-  constexpr int STAGE_BYTES = (1 + NB_TILES) * TILE_BYTES;
+  constexpr int NSTAGES = (DUAL || BN > 128) ? 4 : 6;
+  constexpr int W_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = TILE_BYTES + NB_TILES * W_BYTES;
   constexpr int ACC_COLS = NB_TILES * BN;             // TMEM columns per accumulator stage
   constexpr uint32_t IDESC = umma_idesc(std::is_same<T, bf16>::value ? 1 : 0, BM, BN);
 
@@ -84,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m_blk * BM);
           tma_load_2d(sa + TILE_BYTES, &map_w, full_bar(stage), kb * BK, n_blk * BN);
-          if (DUAL) tma_load_2d(sa + 2 * TILE_BYTES, &map_w, full_bar(stage), kb * BK, p.N + n_blk * BN);
+          if (DUAL) tma_load_2d(sa + TILE_BYTES + W_BYTES, &map_w, full_bar(stage), kb * BK, p.N + n_blk * BN);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -107,7 +108,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t ad = umma_desc(sa + k * UMMA_K * 2);
             const uint32_t accumulate = (kb > 0 || k > 0) ? 1u : 0u;
             umma(d_tmem, ad, umma_desc(sa + TILE_BYTES + k * UMMA_K * 2), IDESC, accumulate);
-            if (DUAL) umma(d_tmem + BN, ad, umma_desc(sa + 2 * TILE_BYTES + k * UMMA_K * 2), IDESC, accumulate);
+            if (DUAL) umma(d_tmem + BN, ad, umma_desc(sa + TILE_BYTES + W_BYTES + k * UMMA_K * 2), IDESC, accumulate);
           }
           umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
@@ -212,13 +213,13 @@ bool make_map_2d(CUtensorMap* map, const void* base, long long rows, long long c
   return r == CUDA_SUCCESS;
 }
 
-template <typename T, int EPI>
+template <typename T, int EPI, int BN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
   constexpr bool DUAL = (EPI == PG_EPI_GEGLU);
-  constexpr int NSTAGES = DUAL ? 4 : 6;
-  constexpr int STAGE_BYTES = (DUAL ? 3 : 2) * TILE_BYTES;
+  constexpr int NSTAGES = (DUAL || BN > 128) ? 4 : 6;
+  constexpr int STAGE_BYTES = TILE_BYTES + (DUAL ? 2 : 1) * BN * BK * 2;
   const size_t smem = 1024 + (size_t)NSTAGES * STAGE_BYTES + 8 * (2 * NSTAGES + 4) + 16;
-  auto kern = gemm_tc_kernel<T, EPI>;
+  auto kern = gemm_tc_kernel<T, EPI, BN>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     set_error("gemm_tc: cannot reserve %zu B of shared memory", smem);
     cudaGetLastError();
@@ -248,13 +249,22 @@ int gemm_tc(void* C, const void* A, const void* W, const void* bias, const void*
   PG_REQUIRE(!R || (((uintptr_t)R % 16) == 0 && ldr % 8 == 0), "gemm_tc: residual must be 16-byte aligned rows");
   PG_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_tc: bias must be 16-byte aligned");
   const bool bf = dtype == PG_BF16;
+  // 64-wide N tiles when 128-wide ones would occupy well under one wave of the 148 SMs
+  static const int bn_env = env_int("PG_GEMM_BN", 0);
+  // and 256-wide ones (half the A-operand shared-memory traffic per FLOP) when there is work for > 2 waves
+  int bn = bn_env ? bn_env : ((cdiv(M, tc::BM) * cdiv(N, 128) < 100) ? 64 : (cdiv(M, tc::BM) * cdiv(N, 256) >= 296 ? 256 : 128));
+  if (epi == PG_EPI_GEGLU && bn == 256) bn = 128;  // gate+up already fill 512 TMEM columns at 128
   CUtensorMap ma, mw;
   const int w_rows = (epi == PG_EPI_GEGLU) ? 2 * N : N;
-  PG_REQUIRE(tc::make_map_2d(&ma, A, M, K, lda, tc::BM, bf) && tc::make_map_2d(&mw, W, w_rows, K, ldw, tc::BN, bf),
+  PG_REQUIRE(tc::make_map_2d(&ma, A, M, K, lda, tc::BM, bf) && tc::make_map_2d(&mw, W, w_rows, K, ldw, bn, bf),
              "gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", M, N, K, lda, ldw);
   tc::Params p = {C, bias, R, M, N, K, ldc, ldr, res_mod, out_f32};
-#define PG_TC(E) \
-  return bf ? tc::launch<bf16, E>(ma, mw, p, st) : tc::launch<f16, E>(ma, mw, p, st)
+#define PG_TC(E)                                                                                       \
+  if (bn == 64) return bf ? tc::launch<bf16, E, 64>(ma, mw, p, st) : tc::launch<f16, E, 64>(ma, mw, p, st); \
+  if (bn == 256 && E != PG_EPI_GEGLU)                                                                    \
+    return bf ? tc::launch<bf16, (E == PG_EPI_GEGLU ? PG_EPI_NONE : E), 256>(ma, mw, p, st)              \
+              : tc::launch<f16, (E == PG_EPI_GEGLU ? PG_EPI_NONE : E), 256>(ma, mw, p, st);              \
+  return bf ? tc::launch<bf16, E, 128>(ma, mw, p, st) : tc::launch<f16, E, 128>(ma, mw, p, st)
   switch (epi) {
     case PG_EPI_NONE: PG_TC(PG_EPI_NONE);
     case PG_EPI_BIAS: PG_TC(PG_EPI_BIAS);
