@@ -200,6 +200,15 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.f + tanhf(inner));
 }
 
+// Same formula with the hardware tanh (MUFU.TANH, rel. error ~2^-11): used only by the 16-bit tensor-core
+// epilogues, whose outputs are rounded to 8-11 mantissa bits anyway; the fp32 verification path keeps tanhf.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float inner = 0.7978845608028654f * (x + 0.044715f * (x * x * x));
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  return 0.5f * x * (1.f + t);
+}
+
 // Orderable 64-bit key for (value, index) argmax: larger value wins, ties go to the LOWER index
 // (torch.argmax returns the first maximal element).
 __device__ __forceinline__ unsigned long long argmax_key(float v, unsigned idx) {

@@ -163,6 +163,62 @@ __global__ void layernorm_kernel(T* __restrict__ out, const T* __restrict__ x, c
   }
 }
 
+
+// ------------------------------------------------------------------ warp-per-row norms (many rows)
+// Prefill / vision: thousands of rows of 1152-2048 elements.  One warp per row (8 rows per CTA), the row
+// stays in registers between the statistics and the write, fully coalesced 16-byte accesses.
+template <typename T, int MAXV, bool LAYERNORM>
+__global__ void __launch_bounds__(256)
+norm_rows_warp_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
+                      int rows, int D, float eps) {
+  constexpr int V = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + (size_t)row * D;
+  T* orow = out + (size_t)row * D;
+  float f[MAXV][V];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int c = (j * 32 + lane) * V;
+    if (c < D) {
+      unpack<T>(ldg_cached(xr + c), f[j]);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s += LAYERNORM ? f[j][i] : f[j][i] * f[j][i];
+    }
+  }
+  s = warp_sum(s);
+  float mean = 0.f, scale;
+  if (LAYERNORM) {
+    mean = s / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int c = (j * 32 + lane) * V;
+      if (c < D)
+#pragma unroll
+        for (int i = 0; i < V; ++i) { const float d = f[j][i] - mean; q += d * d; }
+    }
+    scale = rsqrtf(warp_sum(q) / (float)D + eps);
+  } else {
+    scale = rsqrtf(s / (float)D + eps);
+  }
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int c = (j * 32 + lane) * V;
+    if (c < D) {
+      float g[V], bb[V];
+      unpack<T>(ldg_cached(w + c), g);
+      if (LAYERNORM) unpack<T>(ldg_cached(b + c), bb);
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        f[j][i] = LAYERNORM ? (f[j][i] - mean) * scale * g[i] + bb[i] : (f[j][i] * scale) * (1.0f + g[i]);
+      *reinterpret_cast<uint4*>(orow + c) = pack<T>(f[j]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ im2col (stride == kernel)
 template <typename T>
 __global__ void im2col_kernel(T* __restrict__ out, const T* __restrict__ px, int C, int H, int W, int p,
@@ -312,7 +368,11 @@ int pg_rmsnorm(void* out, const void* x, const void* w, int rows, int D, float e
   PG_DISPATCH_DTYPE(dtype, T, {
     constexpr int V = Vec<T>::N;
     PG_REQUIRE(D % V == 0 && D <= 256 * V * 4, "rmsnorm: unsupported D=%d", D);
-    rmsnorm_kernel<T, 4><<<rows, 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w, D, eps);
+    if (rows >= 64 && D <= 32 * V * 8)
+      norm_rows_warp_kernel<T, 8, false><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
+                                                                                        nullptr, rows, D, eps);
+    else
+      rmsnorm_kernel<T, 4><<<rows, 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w, D, eps);
   });
   return check_launch("rmsnorm");
 }
@@ -323,8 +383,12 @@ int pg_layernorm(void* out, const void* x, const void* w, const void* b, int row
   PG_DISPATCH_DTYPE(dtype, T, {
     constexpr int V = Vec<T>::N;
     PG_REQUIRE(D % V == 0 && D <= 256 * V * 4, "layernorm: unsupported D=%d", D);
-    layernorm_kernel<T, 4><<<rows, 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
-                                                                   (const T*)b, D, eps);
+    if (rows >= 64 && D <= 32 * V * 8)
+      norm_rows_warp_kernel<T, 8, true><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
+                                                                                       (const T*)b, rows, D, eps);
+    else
+      layernorm_kernel<T, 4><<<rows, 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
+                                                                     (const T*)b, D, eps);
   });
   return check_launch("layernorm");
 }

@@ -154,8 +154,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               float x = v[j0 + j];
               if (EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES) x += bb[j];
               x = rnd<T>(x);
-              if (EPI == PG_EPI_BIAS_GELU) x = rnd<T>(gelu_tanh(x));
-              if (EPI == PG_EPI_GEGLU) x = rnd<T>(rnd<T>(gelu_tanh(x)) * rnd<T>(u[DUAL ? j0 + j : 0]));
+              if (EPI == PG_EPI_BIAS_GELU) x = rnd<T>(gelu_tanh_fast(x));
+              if (EPI == PG_EPI_GEGLU) x = rnd<T>(rnd<T>(gelu_tanh_fast(x)) * rnd<T>(u[DUAL ? j0 + j : 0]));
               if (EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES) x = rnd<T>(x + rr[j]);
               o[j] = x;
             }

@@ -50,7 +50,7 @@ def st():
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("rows,D", [(5, 128), (3, 2048), (7, 1152)])
+@pytest.mark.parametrize("rows,D", [(5, 128), (3, 2048), (7, 1152), (300, 1152), (260, 2048), (65, 144)])
 def test_rmsnorm_layernorm(dtype, rows, D):
     x, w, b = gen(rows, D, scale=3, dtype=dtype), gen(D, seed=1, scale=0.1, dtype=dtype), gen(D, seed=2, scale=0.1, dtype=dtype)
     out = torch.empty_like(dev(x))
