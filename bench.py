@@ -358,6 +358,45 @@ def run_ours(args, rank, world, local):
                   "steps": len(lat), "prefix_len": N,
                   "note": "each step = SigLIP + projector + unmasked recompute of the whole prefix (ablation_study_fixed.py:245-251)"}
 
+    # ---------------- SigLIP + projector batch encode (configs[2]) and the 260-token prefill, tensor-bound rows
+    vision = prefill = None
+    if args.vision_batch > 0 and world == 1:
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                mp = json.load(f)
+            tpeak, tsus = float(mp["bf16_tflops"]), float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"]))
+        except Exception:
+            tpeak, tsus = 1590.0, 1400.0
+        vb = args.vision_batch
+        pixb = torch.rand(vb, 3, d.S, d.S, device="cuda") * 2 - 1
+        with torch.no_grad():
+            eng.encode_images(pixb)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); eng.encode_images(pixb); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            vms = statistics.median(ts)
+            flop_img = 2.202e11   # SigLIP So400m/14 + projector per 224x224 image
+            vision = {"batch": vb, "ms": vms, "images_per_s": vb / (vms / 1e3), "tflops": vb * flop_img / (vms / 1e3) / 1e12,
+                      "frac_of_bf16_burst_peak": vb * flop_img / (vms / 1e3) / 1e12 / tpeak,
+                      "frac_of_bf16_sustained_peak": vb * flop_img / (vms / 1e3) / 1e12 / tsus,
+                      "flop_per_image": flop_img, "peak_tflops": {"burst": tpeak, "sustained": tsus}}
+            f1 = eng.encode_images(pix_d)
+            eng.text_forward(ids_d, f1, None, logits="last")
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); eng.text_forward(ids_d, f1, None, logits="last"); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            pms = statistics.median(ts)
+            pflop = 2 * N * 1.98e9 + 4 * d.nq * N * N * d.hd * d.L + 2 * d.V * d.D
+            prefill = {"tokens": N, "ms": pms, "tflops": pflop / (pms / 1e3) / 1e12,
+                       "hbm_floor_ms": eng.weight_bytes_per_decode_step() / (peak * 1e9) * 1e3,
+                       "note": "text decoder over the 260-token prompt, last-position logits (weights read once: at the HBM/tensor ridge)"}
+
     # ---------------- CPU baseline (oracle port, bounded sample)
     cpu = None
     if args.cpu_steps > 0 and world == 1:
@@ -387,6 +426,8 @@ def run_ours(args, rank, world, local):
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak}},
         "cpu_baseline": cpu,
         "kv_off": kv_off,
+        "vision_encode": vision,
+        "prefill": prefill,
         "setup_s": {"synthetic_weights_cpu": round(t_weights, 1)},
     }
     print(json.dumps(line), flush=True)
@@ -401,6 +442,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--kv-off-steps", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--vision-batch", type=int, default=64)
     ap.add_argument("--parallel", default="tp", choices=["tp", "replicas"],
                     help="N > 1: tensor-parallel single stream (north star) or independent replicas")
     args = ap.parse_args()

@@ -198,6 +198,158 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// One-shot variant for short, contiguous key sets (SigLIP: 256 patches, head_dim <= 128): all keys and
+// values of the (batch, head) are staged at once, S = Q K^T is a single 128 x 256 accumulator that stays
+// in TMEM (read twice: row max, then exp), P overwrites the K tile in shared memory, O = P V is one
+// more chain of MMAs.  Three dependent steps per CTA instead of a per-tile loop.
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+attention_tc_oneshot_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                            AttnParams p) {
+  constexpr int HDP = 128, KB = 2, TK = 256;                 // padded head dim, 64-column blocks, keys staged
+  constexpr int Q_BYTES = AQ * HDP * 2, KV_BYTES = TK * HDP * 2;  // 32 KB, 64 KB
+  constexpr int S_COL = 0, O_COL = TK;
+  constexpr int FMT = std::is_same<T, bf16>::value ? 1 : 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_q = base, s_k = s_q + Q_BYTES, s_v = s_k + KV_BYTES, s_p = s_k;  // P reuses the K tile
+  const uint32_t bars = s_v + KV_BYTES;
+  const uint32_t bar_ld = bars, bar_s = bars + 8, bar_p = bars + 16, bar_o = bars + 24, tmem_slot = bars + 32;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* p_ptr = smem_raw + (s_p - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z, kvh = h / p.kv_group;
+  const int T_len = p.kv_len_const;
+  const int nv = ((p.hd + 15) / 16) * 16, k_steps = (p.hd + 15) / 16;
+  const int key_steps = (T_len + 15) / 16;                   // 16-key steps of P V that hold real keys
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_ld, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc_s = umma_idesc(FMT, AQ, TK);
+    const uint32_t idesc_o = umma_idesc(FMT, AQ, nv) | (1u << 16);
+    const int row = (int)(b * p.kv_batch_rows);
+    mbar_expect_tx(bar_ld, Q_BYTES + 2 * KV_BYTES);
+    for (int kb = 0; kb < KB; ++kb) {
+      tma_load_2d(s_q + kb * (AQ * 128), &map_q, bar_ld, p.q_col0 + h * p.hd_stride + kb * 64, b * p.q_len + qb * AQ);
+      tma_load_2d(s_k + kb * (TK * 128), &map_kv, bar_ld, p.k_col0 + kvh * p.hd_stride + kb * 64, row);
+      tma_load_2d(s_v + kb * (TK * 128), &map_kv, bar_ld, p.v_col0 + kvh * p.hd_stride + kb * 64, row);
+    }
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    for (int ks = 0; ks < k_steps; ++ks) {
+      const uint32_t off_q = (ks / 4) * (AQ * 128) + (ks % 4) * 32, off_k = (ks / 4) * (TK * 128) + (ks % 4) * 32;
+      umma(tmem_base + S_COL, umma_desc(s_q + off_q), umma_desc(s_k + off_k), idesc_s, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_s);
+    mbar_wait(bar_p, 0);
+    tc_fence_after();
+    for (int ks = 0; ks < key_steps; ++ks) {
+      const uint32_t off_p = (ks / 4) * (AQ * 128) + (ks % 4) * 32;
+      umma(tmem_base + O_COL, umma_desc(s_p + off_p), umma_desc_mn(s_v + ks * 2048, TK * 128), idesc_o, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_o);
+  } else if (warp >= 4) {
+    const int qw = warp & 3, r = qw * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(qw * 32) << 16);
+    const int n_chunks = (T_len + 31) / 32;
+    float m = -INFINITY, l = 0.f;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        float s[32];
+        tmem_ld32(t_row + S_COL + c * 32, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = rnd<T>(s[j]);
+          x = (p.scale_mul != 0.f) ? x * p.scale_mul : rnd<T>(p.scale_mode ? x / p.scale : x * p.scale);
+          s[j] = (c * 32 + j < T_len) ? x : -INFINITY;
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, s[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s[j] = __expf(s[j] - m); l += s[j]; }
+          uint8_t* blk = p_ptr + (c / 2) * (AQ * 128) + r * 128;
+#pragma unroll
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            const int chunk = ((c & 1) * 4 + j0 / 8) ^ (r & 7);
+            *reinterpret_cast<uint4*>(blk + chunk * 16) = pack<T>(s + j0);
+          }
+        }
+      }
+      if (pass == 1 && (n_chunks & 1)) {
+        // the last 16-key MMA step may read the other half of a 64-key block row: keep it finite (zero)
+        uint8_t* blk = p_ptr + (n_chunks / 2) * (AQ * 128) + r * 128;
+#pragma unroll
+        for (int j0 = 0; j0 < 32; j0 += 8)
+          *reinterpret_cast<uint4*>(blk + ((4 + j0 / 8) ^ (r & 7)) * 16) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(bar_p);
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const int qi = qb * AQ + r;
+    const float inv = 1.f / l;
+    T* orow = reinterpret_cast<T*>(p.out) + (size_t)(b * p.q_len + qi) * p.ld_out + (size_t)h * p.hd;
+#pragma unroll 1
+    for (int c = 0; c * 32 < p.hd; ++c) {
+      float o[32];
+      tmem_ld32(t_row + O_COL + c * 32, o);
+      tmem_ld_wait();
+      if (qi < p.q_len) {
+#pragma unroll
+        for (int j0 = 0; j0 < 32; j0 += 8) {
+          if (c * 32 + j0 >= p.hd) break;
+          float w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = o[j0 + j] * inv;
+          *reinterpret_cast<uint4*>(orow + c * 32 + j0) = pack<T>(w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+template <typename T>
+static int launch_attn_oneshot(const CUtensorMap& mq, const CUtensorMap& mkv, const AttnParams& p, int B, cudaStream_t st) {
+  const size_t smem = 1024 + 32768 + 2 * 65536 + 64;
+  auto kern = attention_tc_oneshot_kernel<T>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("attention_tc(oneshot): cannot reserve %zu B of shared memory", smem);
+    cudaGetLastError();
+    return PG_ERR_CUDA;
+  }
+  dim3 grid(cdiv(p.q_len, AQ), p.n_heads, B);
+  kern<<<grid, 256, smem, st>>>(mq, mkv, p);
+  return check_launch("attention_tc_oneshot");
+}
+
 template <typename T, int HDP, int KT>
 static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int B,
                        cudaStream_t st) {
@@ -247,6 +399,12 @@ extern "C" int pg_attention_tc(void* out, int ld_out, const void* q, long long q
   int ex = 0;
   if (scale_mode == 1 && frexpf(scale, &ex) == 0.5f) p.scale_mul = 1.0f / scale;  // x / 2^k == x * 2^-k exactly
   cudaStream_t st = (cudaStream_t)stream;
+  static const int oneshot = env_int("PG_ATTN_ONESHOT", 0);  // measured slower than the tiled kernel at 2 CTAs/SM (29.5 vs 34.4 ms, batch 64)
+  if (oneshot && hdp == 128 && !page_table && !kv_len && kv_len_const <= 256 && k == v) {
+    CUtensorMap mkv;
+    PG_REQUIRE(tc::make_map_2d(&mkv, k, kv_rows, ld_kv, ld_kv, 256, bf), "attention_tc: cuTensorMapEncodeTiled failed");
+    return bf ? tc::launch_attn_oneshot<bf16>(mq, mkv, p, B, st) : tc::launch_attn_oneshot<f16>(mq, mkv, p, B, st);
+  }
   if (hdp == 128) return bf ? tc::launch_attn<bf16, 128, 64>(mq, mk, mv, p, B, st) : tc::launch_attn<f16, 128, 64>(mq, mk, mv, p, B, st);
   return bf ? tc::launch_attn<bf16, 256, 64>(mq, mk, mv, p, B, st) : tc::launch_attn<f16, 256, 64>(mq, mk, mv, p, B, st);
 }
