@@ -242,6 +242,11 @@ bool gemm_tc_supported(int M, int N, int K, int lda, int ldw, int ldc, int epi, 
   return tc::encode_fn() != nullptr;
 }
 
+int gemm_tc_splitk_factor(int M, int N, int K, int epi, int* bn_out);
+int gemm_tc_splitk(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
+                   int ldw, int ldc, int ldr, int res_mod, int epi, int out_f32, int dtype, int bn, int s,
+                   cudaStream_t st);
+
 int gemm_tc(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
             int ldw, int ldc, int ldr, int res_mod, int epi, int out_f32, int dtype, cudaStream_t st) {
   PG_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)C % 16) == 0,
@@ -249,6 +254,11 @@ int gemm_tc(void* C, const void* A, const void* W, const void* bias, const void*
   PG_REQUIRE(!R || (((uintptr_t)R % 16) == 0 && ldr % 8 == 0), "gemm_tc: residual must be 16-byte aligned rows");
   PG_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_tc: bias must be 16-byte aligned");
   const bool bf = dtype == PG_BF16;
+  {
+    int sk_bn = 0;
+    const int s = gemm_tc_splitk_factor(M, N, K, epi, &sk_bn);  // few tiles, long K: a cluster shares each tile
+    if (s) return gemm_tc_splitk(C, A, W, bias, R, M, N, K, lda, ldw, ldc, ldr, res_mod, epi, out_f32, dtype, sk_bn, s, st);
+  }
   // 64-wide N tiles when 128-wide ones would occupy well under one wave of the 148 SMs
   static const int bn_env = env_int("PG_GEMM_BN", 0);
   // and 256-wide ones (half the A-operand shared-memory traffic per FLOP) when there is work for > 2 waves
