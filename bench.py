@@ -295,6 +295,36 @@ def run_ours(args, rank, world, local):
     ctx_mid = N + W + K // 2
     kv.release()
 
+    # ---------------- N > 1, replicas mode: also time the tensor-parallel decoder (north star sharding)
+    tp_block = None
+    if world > 1 and not use_tp:
+        tp2 = TP(rank, world, None)
+        model_tp = build_model(cfg, {k: v.data for k, v in model.state_dict().items()}, dtype, tp2)
+        eng_tp = model_tp._engine_ready()
+        kv2 = eng_tp.new_kv(B)
+        kv2.reserve(N + W + K + 8)
+        with torch.no_grad():
+            lg2 = eng_tp.text_forward(ids_d, eng_tp.encode_images(pix_d), kv2, logits="last")
+        ds2 = eng_tp.decode_state(B)
+        ds2.want_full_logits = False
+        ds2.bind(kv2, lg2[:, -1].argmax(-1), position=N + 1)
+        for _ in range(W):
+            ds2.run_steps(kv2, 1)
+        barrier(world)
+        g2 = next(iter(ds2.graphs.values()))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(K):
+            g2.replay()
+        a1.record()
+        torch.cuda.synchronize()
+        tp_ms = max_over_ranks(a0.elapsed_time(a1), world)
+        tp_block = {"value": B * K / (tp_ms / 1e3), "unit": UNIT, "ms_per_step": tp_ms / K, "scaling": "strong",
+                    "parallelism": f"tp{world}: q/o by head, gate/up/down by feature, lm_head by vocab; 36 NCCL all-reduces "
+                                   "+ 1 all-gather of (max,index) pairs per step; K/V replicated",
+                    "bytes_per_rank_per_step": eng_tp.weight_bytes_per_decode_step()}
+        kv2.release()
+
     # ---------------- e2e through the reference-facing API with host buffers
     e2e = None
     if rank == 0 or world > 1:
@@ -421,11 +451,13 @@ def run_ours(args, rank, world, local):
         "launches_per_step": launches_per_step,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": "decode_gateup_kernel (RMSNorm + gate/up GEMV + GeGLU)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": 137.75e6 if world == 1 else None,   # dram read+write per launch, ncu --set full (profiles/r01_ncu_full_final_gateup.csv)
                      "bytes_per_launch": k_bytes, "ms_per_launch": k_ms, "peak_source": peak_src,
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak}},
         "cpu_baseline": cpu,
         "kv_off": kv_off,
+        "tensor_parallel": tp_block,
         "vision_encode": vision,
         "prefill": prefill,
         "setup_s": {"synthetic_weights_cpu": round(t_weights, 1)},
@@ -443,8 +475,10 @@ def main():
     ap.add_argument("--kv-off-steps", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--vision-batch", type=int, default=64)
-    ap.add_argument("--parallel", default="tp", choices=["tp", "replicas"],
-                    help="N > 1: tensor-parallel single stream (north star) or independent replicas")
+    ap.add_argument("--parallel", default="replicas", choices=["tp", "replicas"],
+                    help="N > 1: what `value` measures. replicas = one independent sequence per GPU (weak scaling, no "
+                         "data-path collective); tp = ONE sequence, tensor-parallel decoder over NCCL (strong scaling). "
+                         "With replicas the tensor-parallel step is measured too and reported under `tensor_parallel`.")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
