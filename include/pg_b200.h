@@ -174,6 +174,14 @@ int pg_top_p_sample(int64_t* out, const float* logits, float* probs_ws, int B, i
                     float temperature, float top_p, unsigned long long seed,
                     const int* rng_offset, int* nucleus_size, void* stream);
 
+/* Tensor-parallel decoder: one-shot all-reduce(sum) of a small vector over NVLink peer memory (replaces the
+ * NCCL all-reduce after o_proj / down_proj when the message is a few KB).  peers_dev: device array of `tp`
+ * pointers to the ranks' symmetric buffers (each 2*cap_bytes of data slots + 2*16 uint32 flags, zeroed once);
+ * step_counter: device int, the same on every rank, advanced by the kernel.  x is reduced in place; every
+ * rank sums in rank order (bit-identical results).  *err_flag = 2 if a peer never arrived. */
+int pg_allreduce_oneshot(void* x, const void* peers_dev, int rank, int tp, int n, long long cap_bytes,
+                         int* step_counter, int* err_flag, int dtype, void* stream);
+
 /* KVCache.key_cache[layer] / value_cache[layer] view: gather pages into a contiguous
  * [B, nkv, T, hd] tensor (modeling_gemma.py:12-36 attribute parity). */
 int pg_kv_gather(void* out, const void* pool, const int32_t* page_table, int pt_stride,

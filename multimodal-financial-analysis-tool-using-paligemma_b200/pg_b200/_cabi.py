@@ -47,6 +47,7 @@ SIGNATURES = {
     "pg_step_advance": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "pg_argmax": [_vp, _vp, _vp, _i, _ll, _vp],
     "pg_top_p_sample": [_vp, _vp, _vp, _i, _ll, _f, _f, _ull, _vp, _vp, _vp],
+    "pg_allreduce_oneshot": [_vp, _vp, _i, _i, _i, _ll, _vp, _vp, _i, _vp],
     "pg_kv_gather": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPE = {"pg_last_error": C.c_char_p, "pg_launch_count": _ull, "pg_decode_attention_ws_floats": _ll}

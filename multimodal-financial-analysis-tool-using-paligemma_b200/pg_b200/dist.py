@@ -14,9 +14,51 @@ from typing import Optional
 import torch
 
 
+class OneShot:
+    """Symmetric (peer-mapped) buffers + step counter for pg_allreduce_oneshot.  torch's symmetric-memory
+    rendezvous is only the plumbing that exchanges the peer mappings; the all-reduce kernel is ours."""
+    CAP = 1 << 16          # bytes per data slot: (B<=8, 2048) bf16/fp32 partials fit
+
+    def __init__(self, rank: int, size: int, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.size = rank, size
+        self.buf = symm.empty(2 * self.CAP + 2 * 16 * 4, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.peers_dev = int(self.hdl.buffer_ptrs_dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier()      # every rank's flags are zero before anyone signals
+
+    def fits(self, t: torch.Tensor) -> bool:
+        return t.is_contiguous() and t.numel() * t.element_size() <= self.CAP and t.numel() % 8 == 0
+
+
 class TP:
     def __init__(self, rank: int = 0, size: int = 1, group=None):
         self.rank, self.size, self.group = rank, size, group
+        self.oneshot = None
+        self._oneshot_tried = False
+
+    def _maybe_oneshot(self, device):
+        """PG_TP_ALLREDUCE=oneshot selects the peer-memory kernel (parity-green on 2 GPUs, err flag 0); the
+        default stays NCCL: as a separate launch the one-shot kernel measured 1.166 ms/step vs 1.116 ms
+        for NCCL at tp=2 — it only pays once it is fused into the GEMV epilogue (next round)."""
+        import os
+        if self._oneshot_tried:
+            return self.oneshot
+        self._oneshot_tried = True
+        if os.environ.get("PG_TP_ALLREDUCE", "nccl") != "oneshot" or self.size > 16:
+            return None
+        try:
+            self.oneshot = OneShot(self.rank, self.size, device)
+        except Exception as e:  # noqa: BLE001  (no peer access / unsupported allocator: NCCL still works)
+            import warnings
+            warnings.warn(f"one-shot all-reduce unavailable ({e!r}); using NCCL")
+            self.oneshot = None
+        return self.oneshot
 
     @property
     def active(self) -> bool:
@@ -24,6 +66,13 @@ class TP:
 
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.size > 1:
+            one = self._maybe_oneshot(t.device) if t.is_cuda else None
+            if one is not None and one.fits(t):
+                from . import _cabi as cabi
+                cabi.check(cabi.lib().pg_allreduce_oneshot(t.data_ptr(), one.peers_dev, self.rank, self.size, t.numel(),
+                                                           one.CAP, one.step.data_ptr(), one.err.data_ptr(),
+                                                           cabi.DTYPE_CODE[t.dtype], cabi.stream()), "allreduce_oneshot")
+                return t
             import torch.distributed as dist
             dist.all_reduce(t, group=self.group)
         return t

@@ -17,6 +17,7 @@ import modeling_gemma as MG  # noqa: E402
 
 
 def main():
+    os.environ.setdefault("PG_TP_ALLREDUCE", "oneshot")  # exercise the peer-memory all-reduce too (falls back to NCCL)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -53,6 +54,11 @@ def main():
             ok &= good
             print(f"[rank {rank}] {name} tp={world}: tokens {'OK' if toks == g['cached_tokens'].tolist() else toks} "
                   f"api {'OK' if [api] == g['cached_tokens'].tolist() else api} max|dlogit| {err:.2e} (tol {tol:.2e})", flush=True)
+    if tp.oneshot is not None:
+        ok &= int(tp.oneshot.err.item()) == 0
+        print(f"[rank {rank}] one-shot all-reduce used, {int(tp.oneshot.step.item())} calls, err flag {int(tp.oneshot.err.item())}", flush=True)
+    else:
+        print(f"[rank {rank}] NCCL all-reduce path", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     passed = int(flag.item()) == 1
