@@ -196,10 +196,29 @@ def golden_full(dtype, tag: str, steps: int, unc_steps: int):
     np.savez_compressed(os.path.join(OUT, f"full_{tag}.npz"), **out)
 
 
+def golden_processor():
+    """The reference's own PaliGemmaProcessor (processing_paligemma.py:52-117) on a synthetic RGB image and the
+    stub tokenizer: pins resize / rescale / normalise / prompt construction of the drop-in processor."""
+    sys.path.insert(0, REF)
+    import processing_paligemma as ref_proc
+    sys.path.remove(REF)
+    sys.modules.pop("processing_paligemma", None)
+    from PIL import Image
+    yy, xx = np.mgrid[0:480, 0:640]
+    img = Image.fromarray(np.stack([(xx * 255 // 639), (yy * 255 // 479), ((xx + yy) % 256)], -1).astype(np.uint8))
+    proc = ref_proc.PaliGemmaProcessor(synth.StubTokenizer(), 256, 224)
+    out = proc(text=["caption en"], images=[img])
+    np.savez_compressed(os.path.join(OUT, "processor.npz"), pixel_values=out["pixel_values"].numpy(),
+                        input_ids=out["input_ids"].numpy(), attention_mask=out["attention_mask"].numpy())
+    print("processor", out["pixel_values"].shape, out["input_ids"].shape)
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     os.makedirs(OUT, exist_ok=True)
     what = sys.argv[1:] or ["tiny", "small"]
+    if "processor" in what:
+        golden_processor()
     if "tiny" in what:
         golden_small_model("tiny", steps=8)
     if "small" in what:
