@@ -65,6 +65,7 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
         for (int i = 0; i < V; ++i) qf[g][c][i] = 0.f;
     }
   float m[G], l[G], acc[G][NCH][V];
+  float m_run = -INFINITY, l_run = 0.f;   // transposed path: lane L keeps the state of head L % G
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     m[g] = -INFINITY; l[g] = 0.f;
@@ -112,46 +113,110 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
         s[t][g] = a;
       }
     }
+    if constexpr (TB * G == 32) {
+      // 32 (token, head) partial dots per lane -> transposed butterfly: 31 shuffles leave lane L with the full
+      // sum of pair L = t*G + g (instead of 32 x 5 shuffles with every lane holding every sum), so the scale /
+      // max / exp work is done once per pair, not 32 times.
+      float sv[32];
 #pragma unroll
-    for (int t = 0; t < TB; ++t)
+      for (int t = 0; t < TB; ++t)
 #pragma unroll
-      for (int g = 0; g < G; ++g) s[t][g] = warp_sum(s[t][g]);
+        for (int g = 0; g < G; ++g) sv[t * G + g] = s[t][g];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float mn = m[g];
+      for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
 #pragma unroll
-      for (int t = 0; t < TB; ++t) {
-        // matmul output rounded to the model dtype, then "/ sqrt(head_dim)" (modeling_gemma.py:266)
-        // (a power-of-two divisor is applied as an exact multiply: same bits, no division routine)
-        const float sr = rnd<T>(s[t][g]);
-        const float sc = (scale_mul != 0.f) ? sr * scale_mul : rnd<T>(sr / scale_div);
-        s[t][g] = (j0 + t * NW < T_len) ? sc : -INFINITY;
-        mn = fmaxf(mn, s[t][g]);
+        for (int i = 0; i < w; ++i) {
+          const float keep = up ? sv[i + w] : sv[i];
+          const float send = up ? sv[i] : sv[i + w];
+          sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
       }
-      const float corr = __expf(m[g] - mn);
-      m[g] = mn;
-      l[g] *= corr;
+      const int my_t = lane / G;
+      // matmul output rounded to the model dtype, then "/ sqrt(head_dim)" (modeling_gemma.py:266); a power-of-two
+      // divisor is applied as an exact multiply (same bits, no division routine)
+      const float sr = rnd<T>(sv[0]);
+      float sc = (scale_mul != 0.f) ? sr * scale_mul : rnd<T>(sr / scale_div);
+      sc = (j0 + my_t * NW < T_len) ? sc : -INFINITY;
+      float mx = sc;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c)
+      for (int o = G; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));  // over the TB tokens of my head
+      const float mn = fmaxf(m_run, mx);
+      const float corr = __expf(m_run - mn);
+      const float pr = __expf(sc - mn);                      // 0 for padded tokens
+      float psum = pr;
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[g][c][i] *= corr;
+      for (int o = G; o < 32; o <<= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      m_run = mn;
+      l_run = l_run * corr + psum;
 #pragma unroll
-      for (int t = 0; t < TB; ++t) s[t][g] = __expf(s[t][g] - mn);  // p; 0 for the padded tokens
-#pragma unroll
-      for (int t = 0; t < TB; ++t) l[g] += s[t][g];
-    }
-#pragma unroll
-    for (int t = 0; t < TB; ++t) {
-      float vf[NCH][V];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) unpack<T>(vr[t][c], vf[c]);
-#pragma unroll
-      for (int g = 0; g < G; ++g)
+      for (int g = 0; g < G; ++g) {
+        const float cg = __shfl_sync(0xffffffffu, corr, g);
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
-          for (int i = 0; i < V; ++i) acc[g][c][i] = fmaf(s[t][g], vf[c][i], acc[g][c][i]);
+          for (int i = 0; i < V; ++i) acc[g][c][i] *= cg;
+      }
+#pragma unroll
+      for (int t = 0; t < TB; ++t) {
+        float vf[NCH][V];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) unpack<T>(vr[t][c], vf[c]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float pg = __shfl_sync(0xffffffffu, pr, t * G + g);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[g][c][i] = fmaf(pg, vf[c][i], acc[g][c][i]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < TB; ++t)
+  #pragma unroll
+        for (int g = 0; g < G; ++g) s[t][g] = warp_sum(s[t][g]);
+  #pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float mn = m[g];
+  #pragma unroll
+        for (int t = 0; t < TB; ++t) {
+          // matmul output rounded to the model dtype, then "/ sqrt(head_dim)" (modeling_gemma.py:266)
+          // (a power-of-two divisor is applied as an exact multiply: same bits, no division routine)
+          const float sr = rnd<T>(s[t][g]);
+          const float sc = (scale_mul != 0.f) ? sr * scale_mul : rnd<T>(sr / scale_div);
+          s[t][g] = (j0 + t * NW < T_len) ? sc : -INFINITY;
+          mn = fmaxf(mn, s[t][g]);
+        }
+        const float corr = __expf(m[g] - mn);
+        m[g] = mn;
+        l[g] *= corr;
+  #pragma unroll
+        for (int c = 0; c < NCH; ++c)
+  #pragma unroll
+          for (int i = 0; i < V; ++i) acc[g][c][i] *= corr;
+  #pragma unroll
+        for (int t = 0; t < TB; ++t) s[t][g] = __expf(s[t][g] - mn);  // p; 0 for the padded tokens
+  #pragma unroll
+        for (int t = 0; t < TB; ++t) l[g] += s[t][g];
+      }
+  #pragma unroll
+      for (int t = 0; t < TB; ++t) {
+        float vf[NCH][V];
+  #pragma unroll
+        for (int c = 0; c < NCH; ++c) unpack<T>(vr[t][c], vf[c]);
+  #pragma unroll
+        for (int g = 0; g < G; ++g)
+  #pragma unroll
+          for (int c = 0; c < NCH; ++c)
+  #pragma unroll
+            for (int i = 0; i < V; ++i) acc[g][c][i] = fmaf(s[t][g], vf[c][i], acc[g][c][i]);
+      }
     }
+  }
+  if constexpr (TB * G == 32) {  // the per-head running (m, l) live in the lanes of that head: gather them
+#pragma unroll
+    for (int g = 0; g < G; ++g) { m[g] = __shfl_sync(0xffffffffu, m_run, g); l[g] = __shfl_sync(0xffffffffu, l_run, g); }
   }
 
   // ---- merge the warps of this CTA
@@ -273,14 +338,24 @@ template <typename T, int G, int NCH>
 static int launch_da(void* out, const void* q, const void* k_pool, const void* v_pool, const int32_t* page_table,
                      int pt_stride, int page_size, const int32_t* kv_len, int kv_len_add, int B, int nq, int nkv,
                      int hd, float scale_div, Prefetch pf, cudaStream_t st) {
-  // 16-CTA clusters (non-portable size) halve the per-warp token count; small batches have SMs to spare
+  // Cluster size: as many CTAs per (sequence, kv head) as keeps the whole launch within one wave of the 148 SMs
+  // (the kernel needs a full SM: 255 registers x 256 threads).  16 is a non-portable cluster size.
   static const int ns_env = env_int("PG_ATTN_NS", 0);
-  const int ns = ns_env ? ns_env : (B * nkv <= 8 ? 16 : 8);
-  if (ns == 16)
-    return launch_da_ns<T, G, NCH, 16>(out, q, k_pool, v_pool, page_table, pt_stride, page_size, kv_len, kv_len_add,
-                                       B, nq, nkv, hd, scale_div, pf, st);
-  return launch_da_ns<T, G, NCH, 8>(out, q, k_pool, v_pool, page_table, pt_stride, page_size, kv_len, kv_len_add, B,
-                                    nq, nkv, hd, scale_div, pf, st);
+  int ns = ns_env;
+  if (!ns) {
+    const int seqs = B * nkv;
+    ns = seqs <= 9 ? 16 : (seqs <= 18 ? 8 : (seqs <= 37 ? 4 : (seqs <= 74 ? 2 : 1)));
+  }
+#define PG_DA_NS(N_) \
+  return launch_da_ns<T, G, NCH, N_>(out, q, k_pool, v_pool, page_table, pt_stride, page_size, kv_len, kv_len_add, B, nq, nkv, hd, scale_div, pf, st)
+  switch (ns) {
+    case 16: PG_DA_NS(16);
+    case 8: PG_DA_NS(8);
+    case 4: PG_DA_NS(4);
+    case 2: PG_DA_NS(2);
+    default: PG_DA_NS(1);
+  }
+#undef PG_DA_NS
 }
 
 }  // namespace pg

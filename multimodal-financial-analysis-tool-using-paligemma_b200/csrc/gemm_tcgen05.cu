@@ -28,7 +28,10 @@ struct Params {
   int M, N, K, ldc, ldr, res_mod, out_f32;
 };
 
-template <typename T, int EPI, int BN>
+// CL = 2: CTA pairs (a 2-CTA cluster) work on vertically adjacent tiles (same n_blk, m_blk = 2*mp + rank): each CTA
+// loads its own A tile and HALF of the shared W tile, multicast into both CTAs' shared memory, so the L2->SM
+// traffic per FLOP drops by a third (the 128x256 single-CTA tile needs ~94 B/clk/SM, more than the fabric gives).
+template <typename T, int EPI, int BN, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, Params p) {
   constexpr bool DUAL = (EPI == PG_EPI_GEGLU);
@@ -50,8 +53,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles_real = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  // CL == 2: schedule over (n_blk, m-pair); the CTA's own tile is m_blk = 2*mp + rank (a ghost tile past M loads
+  // zeros and stores nothing).  CL == 1: plain tiles.
+  uint32_t crank = 0;
+  if (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int m_tiles = (CL == 2) ? (m_tiles_real + 1) / 2 : m_tiles_real;   // schedule units along M
   const int total_tiles = m_tiles * n_tiles;
+  const int sched_first = (CL == 2) ? (int)(blockIdx.x / 2) : (int)blockIdx.x;
+  const int sched_stride = (CL == 2) ? (int)(gridDim.x / 2) : (int)gridDim.x;
   const int k_blocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -59,7 +69,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -69,6 +79,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) {  // the peer's barriers must exist before anything is multicast into / arrives on them
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -77,13 +91,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_blk = tile / m_tiles, m_blk = tile % m_tiles;  // neighbours share the W tile (L2 reuse)
+      for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
+        const int n_blk = tile / m_tiles;                          // neighbours share the W tile (L2 reuse)
+        const int m_blk = (CL == 2) ? 2 * (tile % m_tiles) + (int)crank : tile % m_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_wait(empty_bar(stage), phase ^ 1);                  // CL == 2: both CTAs have consumed this stage
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m_blk * BM);
+          if (CL == 2) {  // this CTA's half of the W tile, delivered to both CTAs of the pair
+            tma_load_2d_mcast(sa + TILE_BYTES + crank * (W_BYTES / 2), &map_w, full_bar(stage), kb * BK,
+                              n_blk * BN + (int)crank * (BN / 2), (uint16_t)0x3);
+          } else
           tma_load_2d(sa + TILE_BYTES, &map_w, full_bar(stage), kb * BK, n_blk * BN);
           if (DUAL) tma_load_2d(sa + TILE_BYTES + W_BYTES, &map_w, full_bar(stage), kb * BK, p.N + n_blk * BN);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
@@ -95,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
@@ -110,7 +129,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             umma(d_tmem, ad, umma_desc(sa + TILE_BYTES + k * UMMA_K * 2), IDESC, accumulate);
             if (DUAL) umma(d_tmem + BN, ad, umma_desc(sa + TILE_BYTES + W_BYTES + k * UMMA_K * 2), IDESC, accumulate);
           }
-          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+          if (CL == 2) umma_commit_mcast(empty_bar(stage), (uint16_t)0x3);  // frees the stage in BOTH CTAs
+          else umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar(acc));  // accumulator complete
@@ -126,8 +146,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* Cf = reinterpret_cast<float*>(p.C);
     const T* bias = reinterpret_cast<const T*>(p.bias);
     const T* R = reinterpret_cast<const T*>(p.R);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_blk = tile / m_tiles, m_blk = tile % m_tiles;
+    for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
+      const int n_blk = tile / m_tiles;
+      const int m_blk = (CL == 2) ? 2 * (tile % m_tiles) + (int)crank : tile % m_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int m = m_blk * BM + q * 32 + lane;
@@ -177,6 +198,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) {  // the peer may still multicast into this CTA's shared memory or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -213,17 +238,39 @@ bool make_map_2d(CUtensorMap* map, const void* base, long long rows, long long c
   return r == CUDA_SUCCESS;
 }
 
-template <typename T, int EPI, int BN>
+template <typename T, int EPI, int BN, int CL = 1>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
   constexpr bool DUAL = (EPI == PG_EPI_GEGLU);
   constexpr int NSTAGES = (DUAL || BN > 128) ? 4 : 6;
   constexpr int STAGE_BYTES = TILE_BYTES + (DUAL ? 2 : 1) * BN * BK * 2;
   const size_t smem = 1024 + (size_t)NSTAGES * STAGE_BYTES + 8 * (2 * NSTAGES + 4) + 16;
-  auto kern = gemm_tc_kernel<T, EPI, BN>;
+  auto kern = gemm_tc_kernel<T, EPI, BN, CL>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     set_error("gemm_tc: cannot reserve %zu B of shared memory", smem);
     cudaGetLastError();
     return PG_ERR_CUDA;
+  }
+  if (CL == 2) {
+    const int pairs = cdiv(cdiv(p.M, BM), 2) * cdiv(p.N, BN);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (pairs < 74 ? pairs : 74));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mw, p);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc (2-CTA multicast) launch: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return PG_ERR_CUDA;
+    }
+    return check_launch("gemm_tcgen05_mcast");
   }
   const int tiles = cdiv(p.M, BM) * cdiv(p.N, BN);
   const int grid = tiles < 148 ? tiles : 148;
@@ -264,13 +311,18 @@ int gemm_tc(void* C, const void* A, const void* W, const void* bias, const void*
   // and 256-wide ones (half the A-operand shared-memory traffic per FLOP) when there is work for > 2 waves
   int bn = bn_env ? bn_env : ((cdiv(M, tc::BM) * cdiv(N, 128) < 100) ? 64 : (cdiv(M, tc::BM) * cdiv(N, 256) >= 296 ? 256 : 128));
   if (epi == PG_EPI_GEGLU && bn == 256) bn = 128;  // gate+up already fill 512 TMEM columns at 128
+  static const int mcast_env = env_int("PG_GEMM_MCAST", 1);
+  const bool mcast = mcast_env && bn == 256;
   CUtensorMap ma, mw;
   const int w_rows = (epi == PG_EPI_GEGLU) ? 2 * N : N;
-  PG_REQUIRE(tc::make_map_2d(&ma, A, M, K, lda, tc::BM, bf) && tc::make_map_2d(&mw, W, w_rows, K, ldw, bn, bf),
+  PG_REQUIRE(tc::make_map_2d(&ma, A, M, K, lda, tc::BM, bf) && tc::make_map_2d(&mw, W, w_rows, K, ldw, mcast ? bn / 2 : bn, bf),
              "gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", M, N, K, lda, ldw);
   tc::Params p = {C, bias, R, M, N, K, ldc, ldr, res_mod, out_f32};
 #define PG_TC(E)                                                                                       \
   if (bn == 64) return bf ? tc::launch<bf16, E, 64>(ma, mw, p, st) : tc::launch<f16, E, 64>(ma, mw, p, st); \
+  if (mcast && E != PG_EPI_GEGLU)                                                                        \
+    return bf ? tc::launch<bf16, (E == PG_EPI_GEGLU ? PG_EPI_NONE : E), 256, 2>(ma, mw, p, st)           \
+              : tc::launch<f16, (E == PG_EPI_GEGLU ? PG_EPI_NONE : E), 256, 2>(ma, mw, p, st);           \
   if (bn == 256 && E != PG_EPI_GEGLU)                                                                    \
     return bf ? tc::launch<bf16, (E == PG_EPI_GEGLU ? PG_EPI_NONE : E), 256>(ma, mw, p, st)              \
               : tc::launch<f16, (E == PG_EPI_GEGLU ? PG_EPI_NONE : E), 256>(ma, mw, p, st);              \

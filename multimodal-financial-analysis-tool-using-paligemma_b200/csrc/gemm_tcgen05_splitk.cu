@@ -215,8 +215,12 @@ static int launch_sk_pick(const CUtensorMap& ma, const CUtensorMap& mw, const Sk
 // Split factor for a problem (0 = do not split).  Chosen so tiles*S fills about two waves of 148 SMs and
 // every CTA still has >= 8 K blocks to stream.
 int gemm_tc_splitk_factor(int M, int N, int K, int epi, int* bn_out) {
-  static const int enabled = env_int("PG_SPLITK", 0);  // off: at M~260 the GEMM is L2->SM bound (every W tile re-read per m-tile), not SM-count bound; measured 6% slower
-  if (!enabled || epi == PG_EPI_GEGLU) return 0;
+  // PG_SPLITK: 0 never, 1 always when it applies, default (-1): only for a single row of tiles (M <= 128, the
+  // batched-decode GEMMs): there W is read once anyway and the only problem is that 16-40 CTAs cannot pull
+  // 6 TB/s.  With several m-tiles (260-token prefill) the GEMM is L2->SM bound and splitting measured 6 % slower.
+  static const int mode = env_int("PG_SPLITK", -1);
+  if (mode == 0 || epi == PG_EPI_GEGLU) return 0;
+  if (mode < 0 && M > tc::SK_BM) return 0;
   const int bn = N <= 4096 ? 64 : 128;
   const int tiles = cdiv(M, tc::SK_BM) * cdiv(N, bn), kb = cdiv(K, tc::SK_BK);
   if (tiles >= 120) return 0;

@@ -14,7 +14,10 @@
 
 namespace pg {
 
-constexpr int GEMV_THREADS = 256;
+#ifndef PG_GEMV_THREADS
+#define PG_GEMV_THREADS 256
+#endif
+constexpr int GEMV_THREADS = PG_GEMV_THREADS;
 constexpr int GEMV_WARPS = GEMV_THREADS / 32;
 
 // One pipeline stage: U 128-bit vectors of each of R weight rows (this lane's share).

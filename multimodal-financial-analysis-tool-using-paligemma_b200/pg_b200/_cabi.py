@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpg_b200.so")
+LIB_PATH = os.environ.get("PG_LIB_PATH") or os.path.join(_HERE, "libpg_b200.so")
 
 PG_F32, PG_BF16, PG_F16 = 0, 1, 2
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_RES, EPI_GEGLU = 0, 1, 2, 3, 4, 5

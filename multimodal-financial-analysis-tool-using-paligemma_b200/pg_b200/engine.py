@@ -479,6 +479,8 @@ class DecodeState:
         eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
         B, dt = self.B, self.eng.dt
         cap = self.pf_cap_mb
+        if B > cabi.MAX_DECODE_BATCH and not eng.tp.active:
+            return self._launch_step_batched(kv, sample, advance)
         cabi.check(L.pg_embed_merge(ptr(self.x), ptr(self.ids), ptr(eng.emb), None, B, d.D, d.V,
                                     d.image_token_index, d.pad_token_id, 0, eng.img_div, eng.normalizer,
                                     ptr(eng.err_flag), dt, st), "embed")
@@ -549,6 +551,51 @@ class DecodeState:
         if advance:
             cabi.check(L.pg_step_advance(ptr(self.ids), ptr(self.history), self.max_hist, ptr(self.step),
                                          ptr(self.keys), ptr(sampled), ptr(kv.kv_len), ptr(self.pos), B, st),
+                       "step_advance")
+
+    def _launch_step_batched(self, kv: PagedKV, sample: Optional[tuple], advance: bool) -> None:
+        """Decode step for batches above the GEMV tile (BASELINE configs[3]: batch 32): the projections run as
+        skinny GEMMs (tcgen05 for 16-bit dtypes: weights stream through TMA once for the whole batch), attention
+        stays the cluster kernel.  Same rounding points as the GEMV path; capturable (static buffers)."""
+        eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
+        B, dt = self.B, self.eng.dt
+        if not hasattr(self, "bn"):
+            self.bn = eng._new(B, d.D)
+            self.bqkv = eng._new(B, (d.nq + 2 * d.nkv) * d.hd)
+            self.bh = eng._new(B, d.D)
+        cabi.check(L.pg_embed_merge(ptr(self.x), ptr(self.ids), ptr(eng.emb), None, B, d.D, d.V,
+                                    d.image_token_index, d.pad_token_id, 0, eng.img_div, eng.normalizer,
+                                    ptr(eng.err_flag), dt, st), "embed")
+        scale_div = float(math.sqrt(d.hd))
+        x, x2, n = self.x, self.x2, self.bn
+        for li, w in enumerate(eng.t_layers):
+            kp, vp = eng.k_pool[li], eng.v_pool[li]
+            cabi.check(L.pg_rmsnorm(ptr(n), ptr(x), ptr(w["ln1"]), B, d.D, d.eps, dt, st), "rmsnorm")
+            eng._gemm(self.bqkv, n, w["qkv"])
+            cabi.check(L.pg_rope_append(ptr(self.q), ptr(self.bqkv), ptr(eng.inv_freq), ptr(self.pos), ptr(kp), ptr(vp),
+                                        ptr(kv.page_table), kv.max_pages, eng.page_size, ptr(kv.kv_len), B, 1, d.nq, d.nkv,
+                                        d.hd, d.max_pos, dt, st), "rope_append")
+            cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
+                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, d.nq, d.nkv, d.hd,
+                                             scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
+                       "decode_attention")
+            eng._gemm(x2, self.att, w["o"], None, x, cabi.EPI_RES)
+            cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), B, d.D, d.eps, dt, st), "rmsnorm")
+            eng._gemm(self.g, n, w["gu"], None, None, cabi.EPI_GEGLU)
+            eng._gemm(x, self.g, w["down"], None, x2, cabi.EPI_RES)
+        cabi.check(L.pg_rmsnorm(ptr(self.bh), ptr(x), ptr(eng.final_norm), B, d.D, d.eps, dt, st), "final norm")
+        eng._gemm(self.logits, self.bh, eng.lm_head, out_f32=True)
+        if sample is not None:
+            temperature, top_p, seed = sample
+            if self.probs is None:
+                self.probs = torch.empty_like(self.logits)
+            cabi.check(L.pg_top_p_sample(ptr(self.sampled), ptr(self.logits), ptr(self.probs), B, d.V,
+                                         float(temperature), float(top_p), int(seed), ptr(self.step), None, st), "top_p")
+        else:
+            cabi.check(L.pg_argmax(ptr(self.sampled), ptr(self.logits), ptr(self.keys), B, d.V, st), "argmax")
+        if advance:
+            cabi.check(L.pg_step_advance(ptr(self.ids), ptr(self.history), self.max_hist, ptr(self.step),
+                                         ptr(self.keys), ptr(self.sampled), ptr(kv.kv_len), ptr(self.pos), B, st),
                        "step_advance")
 
     def bind(self, kv: PagedKV, next_ids: torch.Tensor, position: int) -> None:

@@ -423,3 +423,29 @@ def test_attention_tc_gemma_paged(dtype, B, q, T, nq):
                                           rows, nkv * hd, 0, 0, hd, 0, pt.data_ptr(), npg, page, kvl.data_ptr(), 0, q, B, q, nq,
                                           nkv, hd, float(math.sqrt(hd)), 1, cabi.DTYPE_CODE[dtype], st()))
     close(out, want, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(4096, 4304, 1152), (4100, 2560, 512), (16384, 1152, 4304)])
+@pytest.mark.parametrize("epi", ["bias", "bias_gelu", "bias_res", "f32"])
+def test_gemm_tcgen05_large_m_multicast_pairs(dtype, M, N, K, epi):
+    """Large-M shapes take the 128x256 tiles with 2-CTA clusters and TMA-multicast W halves (odd m-tile counts
+    exercise the ghost tile of the last pair)."""
+    a = gen(M, K, dtype=dtype)
+    w = gen(N, K, seed=1, scale=1.0 / math.sqrt(K), dtype=dtype)
+    bias, res = gen(N, seed=3, scale=0.1, dtype=dtype), gen(M, N, seed=4, dtype=dtype)
+    code = dict(bias=cabi.EPI_BIAS, bias_gelu=cabi.EPI_BIAS_GELU, bias_res=cabi.EPI_BIAS_RES, f32=cabi.EPI_NONE)[epi]
+    ad, wd, bd, rd = dev(a), dev(w), dev(bias), dev(res)
+    if epi == "bias":
+        want = F.linear(a, w, bias)
+    elif epi == "bias_gelu":
+        want = F.gelu(F.linear(a, w, bias), approximate="tanh")
+    elif epi == "bias_res":
+        want = F.linear(a, w, bias) + res
+    else:
+        want = F.linear(a, w).float()
+    out = torch.full((M, N), float("nan"), dtype=torch.float32 if epi == "f32" else dtype, device="cuda")
+    cabi.check(cabi.lib().pg_gemm(out.data_ptr(), ad.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), M, N, K, K, K,
+                                  N, N, 0, code, 1 if epi == "f32" else 0, 2, cabi.DTYPE_CODE[dtype], st()))
+    torch.cuda.synchronize()
+    close(out, want, dtype)

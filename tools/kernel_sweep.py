@@ -56,6 +56,15 @@ def main():
     nl = len(eng.t_layers)
     e = 2
     res = {}
+    if B > cabi.MAX_DECODE_BATCH:   # batched step only (skinny-GEMM path)
+        ds.run_steps(kv, 1)
+        g = next(iter(ds.graphs.values()))
+        med, mn = timeit(lambda: [g.replay() for _ in range(10)], 10)
+        res = {"batch": B, "context": T, "graph_step_us": {"median": round(med, 1), "min": round(mn, 1)},
+               "tokens_per_s": round(B / (med * 1e-6), 1), "step_bytes": eng.weight_bytes_per_decode_step()}
+        res["step_frac_of_6555"] = round((res["step_bytes"] + B * d.L * 2 * d.hd * 2 * T) / (med * 1e-6) / 1e9 / 6555.2, 4)
+        print(json.dumps(res))
+        return
 
     def rec(name, fn, nbytes):
         med, mn = timeit(fn, nl)
