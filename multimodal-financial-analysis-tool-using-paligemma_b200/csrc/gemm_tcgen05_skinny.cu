@@ -27,11 +27,11 @@ __device__ __forceinline__ void sn_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float sn_ld_dsmem(uint32_t local_addr, uint32_t rank) {
+__device__ __forceinline__ float4 sn_ld_dsmem_v4(uint32_t local_addr, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
   return v;
 }
 
@@ -59,7 +59,9 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * NSTAGES + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* part = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));  // [NT][128] fp32 (S > 1)
+  // S > 1: fp32 partial D^T, one padded row per feature ([128][NT+4]: 16-byte accesses, conflict-free), reusing the ring
+  constexpr int PROW = NT + 4;
+  float* part = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t crank = 0;
@@ -186,7 +188,9 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           tmem_ld16(t_lane + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) part[(c * 16 + j) * 128 + r] = have_k ? v[j] : 0.f;
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(&part[r * PROW + c * 16 + j]) =
+                have_k ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
@@ -199,10 +203,19 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         float v[16], u[DUAL ? 16 : 1];
         tmem_ld16(t_lane + c * 16, v);
         tmem_ld_wait();
+        float4 pv[S > 1 ? S - 1 : 1][4];
+#pragma unroll
+        for (int peer = 1; peer < S; ++peer)   // all remote loads in flight before the first add
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            pv[peer - 1][j] = sn_ld_dsmem_v4(smem_base + (uint32_t)((r * PROW + c * 16 + 4 * j) * 4), peer);
 #pragma unroll
         for (int peer = 1; peer < S; ++peer)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += sn_ld_dsmem(smem_base + (uint32_t)(((c * 16 + j) * 128 + r) * 4), peer);
+          for (int j = 0; j < 4; ++j) {
+            v[4 * j] += pv[peer - 1][j].x; v[4 * j + 1] += pv[peer - 1][j].y;
+            v[4 * j + 2] += pv[peer - 1][j].z; v[4 * j + 3] += pv[peer - 1][j].w;
+          }
         finish(tile, v, u, c * 16);
       }
     }
@@ -272,8 +285,14 @@ static int launch_sn_nt(const CUtensorMap& mx, const CUtensorMap& mw, const SnPa
 }  // namespace tc
 
 bool gemm_tc_skinny_wanted(int M, int N, int K, int epi) {
-  static const int enabled = env_int("PG_SKINNY", 1);
-  return enabled && M >= 16 && M <= 128 && N >= 512 && K >= 256 && epi >= PG_EPI_NONE && epi <= PG_EPI_GEGLU;
+  // Measured on the batch-32 decode step (tools/kernel_sweep.py, SWEEP_B=32): the swap-AB stream wins where a CTA
+  // owns whole weight tiles (gate/up 26.6 vs 29.0 us, lm_head 181 vs 211 us) and for q/k/v (9.9 vs 18.3 us); with a
+  // residual epilogue and a K split (o_proj, down_proj: 16 tiles) the row-major split-K kernel is faster.
+  static const int mode = env_int("PG_SKINNY", 1);   // 0 off, 1 where it wins, 2 everywhere it applies
+  if (!mode || M < 16 || M > 128 || N < 512 || K < 256 || epi < PG_EPI_NONE || epi > PG_EPI_GEGLU) return false;
+  if (mode == 2) return true;
+  const int n_tiles = cdiv(N, 128);
+  return epi == PG_EPI_GEGLU || epi == PG_EPI_NONE || n_tiles >= 100;
 }
 
 int gemm_tc_skinny(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
@@ -284,7 +303,7 @@ int gemm_tc_skinny(void* C, const void* A, const void* W, const void* bias, cons
   // split K across a cluster until ~148 CTAs stream (each keeps >= 8 K blocks)
   int s = 1;
   if (epi != PG_EPI_GEGLU)
-    while (s < 8 && n_tiles * s * 2 <= 160 && kb / (s * 2) >= 8) s *= 2;
+    while (s < 4 && n_tiles * s * 2 <= 160 && kb / (s * 2) >= 8) s *= 2;
   CUtensorMap mx, mw;
   const int w_rows = (epi == PG_EPI_GEGLU) ? 2 * N : N;
   PG_REQUIRE(tc::make_map_2d(&mx, A, M, K, lda, nt, bf) && tc::make_map_2d(&mw, W, w_rows, K, ldw, tc::SN_BM, bf),

@@ -455,7 +455,7 @@ def test_gemm_tcgen05_large_m_multicast_pairs(dtype, M, N, K, epi):
 @pytest.mark.parametrize("M", [16, 32, 33, 64, 100])
 @pytest.mark.parametrize("N,K,epi", [(2560, 2048, "none"), (2048, 2048, "res"), (2048, 16384, "res"), (16384, 2048, "geglu"),
                                      (8064, 2048, "f32"), (4304, 1152, "bias_gelu"), (1152, 4304, "bias_res")])
-def test_gemm_tcgen05_skinny_swap_ab(dtype, M, N, K, epi):
+def test_gemm_tcgen05_skinny_swap_ab(dtype, M, N, K, epi, monkeypatch):
     """Batched-decode shapes (16..128 token rows): the swap-AB weight-streaming kernel, with and without the
     cluster split along K, against torch in the same dtype."""
     if dtype == torch.float16 and M not in (32, 33):
