@@ -200,37 +200,63 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
 
 // ------------------------------------------------------------------------------------------------
-// One-shot variant for short, contiguous key sets (SigLIP: 256 patches, head_dim <= 128): all keys and
-// values of the (batch, head) are staged at once, S = Q K^T is a single 128 x 256 accumulator that stays
-// in TMEM (read twice: row max, then exp), P overwrites the K tile in shared memory, O = P V is one
-// more chain of MMAs.  Three dependent steps per CTA instead of a per-tile loop.
+// ViT attention (SigLIP: <= 256 keys, head_dim <= 80, q/k/v in one fused row-major tensor).
+// One CTA = 128 queries of one (image, head); 2 CTAs per SM overlap each other's load / MMA / softmax phases.
+//   * only the real head columns are staged: columns 0..63 as a SWIZZLE_128B block, columns 64..79 as a
+//     16-column SWIZZLE_32B block (one K step of QK^T, one N=16 slice of PV): 100 KB instead of 160 KB;
+//   * S = Q K^T for all keys is ONE 128 x 256 fp32 accumulator in TMEM (5 MMAs); no second QK^T pass;
+//   * 8 softmax warps: two threads per query row, each owns 128 key columns; row max of the raw accumulators
+//     first (rounding and the positive scale are monotonic), halves exchanged through shared memory, then
+//     exp -> bf16 P written over the dead Q/K tiles; O = P V accumulates into the dead S columns.
+// 256 TMEM columns and ~106 KB of shared memory per CTA.
+constexpr int VIT_TK = 256;
+constexpr int VIT_THREADS = 384;
+
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  // K-major, SWIZZLE_32B: rows of 32 B (one 16-element K step), 8-row groups 256 B apart (SBO)
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_mn_sw32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  // MN-major, SWIZZLE_32B: 16 contiguous MN elements (32 B) per K row, 8-row groups 256 B apart (SBO)
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (16ull << 32) |
+         (1ull << 46) | (6ull << 61);
+}
+__device__ __forceinline__ void vit_softmax_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <typename T>
-__global__ void __launch_bounds__(256, 1)
-attention_tc_oneshot_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                            AttnParams p) {
-  constexpr int HDP = 128, KB = 2, TK = 256;                 // padded head dim, 64-column blocks, keys staged
-  constexpr int Q_BYTES = AQ * HDP * 2, KV_BYTES = TK * HDP * 2;  // 32 KB, 64 KB
-  constexpr int S_COL = 0, O_COL = TK;
+__global__ void __launch_bounds__(VIT_THREADS, 2)
+attention_vit_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map16, AttnParams p) {
   constexpr int FMT = std::is_same<T, bf16>::value ? 1 : 0;
+  // shared memory (offsets from a 1024-byte aligned base); P (64 KB) overlays Q and K once S is complete
+  constexpr uint32_t OFF_Q0 = 0, OFF_Q1 = 16384, OFF_K0 = 20480, OFF_K1 = 53248, OFF_P = 0;
+  constexpr uint32_t OFF_V0 = 65536, OFF_V1 = 98304, OFF_RED = 106496, OFF_BAR = OFF_RED + 2048;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_q = base, s_k = s_q + Q_BYTES, s_v = s_k + KV_BYTES, s_p = s_k;  // P reuses the K tile
-  const uint32_t bars = s_v + KV_BYTES;
-  const uint32_t bar_ld = bars, bar_s = bars + 8, bar_p = bars + 16, bar_o = bars + 24, tmem_slot = bars + 32;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  uint8_t* p_ptr = smem_raw + (s_p - smem_u32(smem_raw));
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t s_q0 = base + OFF_Q0, s_q1 = base + OFF_Q1, s_k0 = base + OFF_K0, s_k1 = base + OFF_K1;
+  const uint32_t s_v0 = base + OFF_V0, s_v1 = base + OFF_V1, s_p = base + OFF_P;
+  const uint32_t bar_qk = base + OFF_BAR, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24, bar_o = bar_qk + 32,
+                 tmem_slot = bar_qk + 40;
+  float* red_m = reinterpret_cast<float*>(base_ptr + OFF_RED);   // [2][128]
+  float* red_l = red_m + 256;                                    // [2][128]
+  uint8_t* p_ptr = base_ptr + OFF_P;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(base_ptr + OFF_BAR + 40);
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z, kvh = h / p.kv_group;
   const int T_len = p.kv_len_const;
-  const int nv = ((p.hd + 15) / 16) * 16, k_steps = (p.hd + 15) / 16;
-  const int key_steps = (T_len + 15) / 16;                   // 16-key steps of P V that hold real keys
+  const bool has_b1 = p.hd > 64;                               // head columns 64..79 exist
+  const int k_steps0 = has_b1 ? 4 : (p.hd + 15) / 16;          // 16-wide K steps inside the 64-column block
+  const int n_s = ((T_len + 15) / 16) * 16;                    // S columns computed
+  const int key_steps = (T_len + 15) / 16;                     // 16-key steps of P V
+  const int n_o0 = has_b1 ? 64 : ((p.hd + 15) / 16) * 16;      // PV output columns from the 64-column V block
 
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_ld, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -239,91 +265,136 @@ attention_tc_oneshot_kernel(const __grid_constant__ CUtensorMap map_q, const __g
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0 && lane == 0) {
-    const uint32_t idesc_s = umma_idesc(FMT, AQ, TK);
-    const uint32_t idesc_o = umma_idesc(FMT, AQ, nv) | (1u << 16);
-    const int row = (int)(b * p.kv_batch_rows);
-    mbar_expect_tx(bar_ld, Q_BYTES + 2 * KV_BYTES);
-    for (int kb = 0; kb < KB; ++kb) {
-      tma_load_2d(s_q + kb * (AQ * 128), &map_q, bar_ld, p.q_col0 + h * p.hd_stride + kb * 64, b * p.q_len + qb * AQ);
-      tma_load_2d(s_k + kb * (TK * 128), &map_kv, bar_ld, p.k_col0 + kvh * p.hd_stride + kb * 64, row);
-      tma_load_2d(s_v + kb * (TK * 128), &map_kv, bar_ld, p.v_col0 + kvh * p.hd_stride + kb * 64, row);
+    // ===================== TMA + MMA issuer (one thread) =====================
+    const int row_q = b * p.q_len + qb * AQ, row_kv = (int)(b * p.kv_batch_rows);
+    const int cq = p.q_col0 + h * p.hd_stride, ck = p.k_col0 + kvh * p.hd_stride, cv = p.v_col0 + kvh * p.hd_stride;
+    mbar_expect_tx(bar_qk, has_b1 ? 61440u : 49152u);
+    tma_load_2d(s_q0, &map64, bar_qk, cq, row_q);
+    tma_load_2d(s_k0, &map64, bar_qk, ck, row_kv);
+    tma_load_2d(s_k0 + 16384, &map64, bar_qk, ck, row_kv + 128);
+    if (has_b1) {
+      tma_load_2d(s_q1, &map16, bar_qk, cq + 64, row_q);
+      tma_load_2d(s_k1, &map16, bar_qk, ck + 64, row_kv);
+      tma_load_2d(s_k1 + 4096, &map16, bar_qk, ck + 64, row_kv + 128);
     }
-    mbar_wait(bar_ld, 0);
+    mbar_expect_tx(bar_v, has_b1 ? 40960u : 32768u);
+    tma_load_2d(s_v0, &map64, bar_v, cv, row_kv);
+    tma_load_2d(s_v0 + 16384, &map64, bar_v, cv, row_kv + 128);
+    if (has_b1) {
+      tma_load_2d(s_v1, &map16, bar_v, cv + 64, row_kv);
+      tma_load_2d(s_v1 + 4096, &map16, bar_v, cv + 64, row_kv + 128);
+    }
+    mbar_wait(bar_qk, 0);
     tc_fence_after();
-    for (int ks = 0; ks < k_steps; ++ks) {
-      const uint32_t off_q = (ks / 4) * (AQ * 128) + (ks % 4) * 32, off_k = (ks / 4) * (TK * 128) + (ks % 4) * 32;
-      umma(tmem_base + S_COL, umma_desc(s_q + off_q), umma_desc(s_k + off_k), idesc_s, ks > 0 ? 1u : 0u);
-    }
+    const uint32_t idesc_s = umma_idesc(FMT, AQ, n_s);
+    for (int ks = 0; ks < k_steps0; ++ks)                      // S = Q K^T
+      umma(tmem_base, umma_desc(s_q0 + ks * 32), umma_desc(s_k0 + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
+    if (has_b1) umma(tmem_base, umma_desc_sw32(s_q1), umma_desc_sw32(s_k1), idesc_s, 1u);
     umma_commit(bar_s);
-    mbar_wait(bar_p, 0);
+    mbar_wait(bar_v, 0);
+    mbar_wait(bar_p, 0);                                       // P complete, every S column has been read
     tc_fence_after();
-    for (int ks = 0; ks < key_steps; ++ks) {
-      const uint32_t off_p = (ks / 4) * (AQ * 128) + (ks % 4) * 32;
-      umma(tmem_base + O_COL, umma_desc(s_p + off_p), umma_desc_mn(s_v + ks * 2048, TK * 128), idesc_o, ks > 0 ? 1u : 0u);
+    const uint32_t idesc_o0 = umma_idesc(FMT, AQ, n_o0) | (1u << 16);  // B (= V) is MN-major
+    const uint32_t idesc_o1 = umma_idesc(FMT, AQ, 16) | (1u << 16);
+    for (int ks = 0; ks < key_steps; ++ks) {                   // O = P V into the dead S columns
+      const uint64_t a = umma_desc(s_p + (ks / 4) * (AQ * 128) + (ks % 4) * 32);
+      umma(tmem_base, a, umma_desc_mn(s_v0 + ks * 2048, VIT_TK * 128), idesc_o0, ks > 0 ? 1u : 0u);
+      if (has_b1) umma(tmem_base + 64, a, umma_desc_mn_sw32(s_v1 + ks * 512, VIT_TK * 32), idesc_o1, ks > 0 ? 1u : 0u);
     }
     umma_commit(bar_o);
   } else if (warp >= 4) {
-    const int qw = warp & 3, r = qw * 32 + lane;
-    const uint32_t t_row = tmem_base + ((uint32_t)(qw * 32) << 16);
-    const int n_chunks = (T_len + 31) / 32;
-    float m = -INFINITY, l = 0.f;
+    // ===================== softmax + epilogue: two threads per query row =====================
+    const int q4 = warp & 3, hf = (warp - 4) >> 2, r = q4 * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const int col0 = hf * 128;
+    const float mul = p.scale_mul != 0.f ? p.scale_mul : p.scale;  // exact power of two, or s*scale rounded to T
+    float s[32];
     mbar_wait(bar_s, 0);
     tc_fence_after();
-    for (int pass = 0; pass < 2; ++pass) {
+    float m = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        float s[32];
-        tmem_ld32(t_row + S_COL + c * 32, s);
+    for (int c = 0; c < 4; ++c) {
+      const int cb = col0 + c * 32;
+      if (cb >= T_len) break;
+      tmem_ld32(t_row + cb, s);
+      tmem_ld_wait();
+      if (cb + 32 <= T_len) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, s[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, cb + j < T_len ? s[j] : -INFINITY);
+      }
+    }
+    red_m[hf * 128 + r] = m;
+    vit_softmax_sync();
+    m = fmaxf(red_m[r], red_m[128 + r]);
+    m = rnd<T>(rnd<T>(m) * mul);                               // the row max after the reference's roundings
+    float l = 0.f;
+    const int t_pad = ((T_len + 63) / 64) * 64;                // P columns the MMAs may touch
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int cb = col0 + c * 32;
+      if (cb >= t_pad) break;
+      if (cb < T_len) {
+        tmem_ld32(t_row + cb, s);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = rnd<T>(s[j]);
-          x = (p.scale_mul != 0.f) ? x * p.scale_mul : rnd<T>(p.scale_mode ? x / p.scale : x * p.scale);
-          s[j] = (c * 32 + j < T_len) ? x : -INFINITY;
+          const float x = rnd<T>(rnd<T>(s[j]) * mul);
+          const float e = __expf(x - m);
+          s[j] = (cb + j < T_len) ? e : 0.f;
+          l += s[j];
         }
-        if (pass == 0) {
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, s[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { s[j] = __expf(s[j] - m); l += s[j]; }
-          uint8_t* blk = p_ptr + (c / 2) * (AQ * 128) + r * 128;
-#pragma unroll
-          for (int j0 = 0; j0 < 32; j0 += 8) {
-            const int chunk = ((c & 1) * 4 + j0 / 8) ^ (r & 7);
-            *reinterpret_cast<uint4*>(blk + chunk * 16) = pack<T>(s + j0);
-          }
-        }
+        for (int j = 0; j < 32; ++j) s[j] = 0.f;
       }
-      if (pass == 1 && (n_chunks & 1)) {
-        // the last 16-key MMA step may read the other half of a 64-key block row: keep it finite (zero)
-        uint8_t* blk = p_ptr + (n_chunks / 2) * (AQ * 128) + r * 128;
+      // P[r][cb .. cb+31] into the K-major SWIZZLE_128B tile: 64-key blocks of 128 rows x 128 B
+      uint8_t* blk = p_ptr + (cb / 64) * (AQ * 128) + r * 128;
 #pragma unroll
-        for (int j0 = 0; j0 < 32; j0 += 8)
-          *reinterpret_cast<uint4*>(blk + ((4 + j0 / 8) ^ (r & 7)) * 16) = make_uint4(0, 0, 0, 0);
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        const int chunk = (((cb / 32) & 1) * 4 + j0 / 8) ^ (r & 7);
+        *reinterpret_cast<uint4*>(blk + chunk * 16) = pack<T>(s + j0);
       }
     }
+    red_l[hf * 128 + r] = l;
     tc_fence_before();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> UMMA
     mbar_arrive(bar_p);
+    vit_softmax_sync();
+    const float inv = 1.f / (red_l[r] + red_l[128 + r]);
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const int qi = qb * AQ + r;
-    const float inv = 1.f / l;
     T* orow = reinterpret_cast<T*>(p.out) + (size_t)(b * p.q_len + qi) * p.ld_out + (size_t)h * p.hd;
-#pragma unroll 1
-    for (int c = 0; c * 32 < p.hd; ++c) {
-      float o[32];
-      tmem_ld32(t_row + O_COL + c * 32, o);
+    // output columns: this thread's half takes [0,48) or [48,80)
+    const int oc0 = hf ? 48 : 0;
+    if (oc0 < p.hd) {
+      tmem_ld32(t_row + oc0, s);
+      float s2[16];
+      if (!hf) tmem_ld16(t_row + 32, s2);
       tmem_ld_wait();
       if (qi < p.q_len) {
 #pragma unroll
         for (int j0 = 0; j0 < 32; j0 += 8) {
-          if (c * 32 + j0 >= p.hd) break;
-          float w[8];
+          if (oc0 + j0 < p.hd) {                               // hd is a multiple of 8
+            float w[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = o[j0 + j] * inv;
-          *reinterpret_cast<uint4*>(orow + c * 32 + j0) = pack<T>(w);
+            for (int j = 0; j < 8; ++j) w[j] = s[j0 + j] * inv;
+            *reinterpret_cast<uint4*>(orow + oc0 + j0) = pack<T>(w);
+          }
+        }
+        if (!hf) {
+#pragma unroll
+          for (int j0 = 0; j0 < 16; j0 += 8) {
+            if (32 + j0 < p.hd) {
+              float w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w[j] = s2[j0 + j] * inv;
+              *reinterpret_cast<uint4*>(orow + 32 + j0) = pack<T>(w);
+            }
+          }
         }
       }
     }
@@ -332,22 +403,22 @@ attention_tc_oneshot_kernel(const __grid_constant__ CUtensorMap map_q, const __g
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
 }
 
 template <typename T>
-static int launch_attn_oneshot(const CUtensorMap& mq, const CUtensorMap& mkv, const AttnParams& p, int B, cudaStream_t st) {
-  const size_t smem = 1024 + 32768 + 2 * 65536 + 64;
-  auto kern = attention_tc_oneshot_kernel<T>;
+static int launch_attn_vit(const CUtensorMap& m64, const CUtensorMap& m16, const AttnParams& p, int B, cudaStream_t st) {
+  const size_t smem = 1024 + 106496 + 2048 + 64;
+  auto kern = attention_vit_kernel<T>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    set_error("attention_tc(oneshot): cannot reserve %zu B of shared memory", smem);
+    set_error("attention_tc(vit): cannot reserve %zu B of shared memory", smem);
     cudaGetLastError();
     return PG_ERR_CUDA;
   }
   dim3 grid(cdiv(p.q_len, AQ), p.n_heads, B);
-  kern<<<grid, 256, smem, st>>>(mq, mkv, p);
-  return check_launch("attention_tc_oneshot");
+  kern<<<grid, VIT_THREADS, smem, st>>>(m64, m16, p);
+  return check_launch("attention_vit");
 }
 
 template <typename T, int HDP, int KT>
@@ -372,7 +443,8 @@ using namespace pg;
 
 // Tensor-core attention.  q/k/v: 16-bit row-major matrices with `*_rows` rows of `ld_*` elements; head h of
 // Q lives at columns q_col0 + h*hd_stride .. +hd (columns hd..hd_stride-1 of a padded head must be zero
-// or belong to memory that multiplies to zero: the kernel always loads ceil(hd/64)*64 columns).
+// or belong to memory that multiplies to zero: the tiled kernel loads ceil(hd/64)*64 columns,
+// the ViT kernel multiplies ceil(hd/16)*16 columns).
 // Output: [B*q_len, ld_out] with head h at column h*hd (packed).
 extern "C" int pg_attention_tc(void* out, int ld_out, const void* q, long long q_rows, int ld_q, int q_col0,
                                const void* k, const void* v, long long kv_rows, int ld_kv, int k_col0, int v_col0,
@@ -387,24 +459,30 @@ extern "C" int pg_attention_tc(void* out, int ld_out, const void* q, long long q
   PG_REQUIRE(n_heads % n_kv_heads == 0, "attention_tc: bad head counts");
   const int hdp = hd <= 128 ? 128 : 256;
   const int kt = 64;
-  PG_REQUIRE(hd == hdp || hd_stride >= ((hd + 63) / 64) * 64 || n_heads == 1, "attention_tc: head rows must be padded to a multiple of 64 columns");
   PG_REQUIRE(!page_table || page_size == kt, "attention_tc: page size must equal the key tile (%d)", kt);
   const bool bf = dtype == PG_BF16;
-  CUtensorMap mq, mk, mv;
-  PG_REQUIRE(tc::make_map_2d(&mq, q, q_rows, ld_q, ld_q, tc::AQ, bf) && tc::make_map_2d(&mk, k, kv_rows, ld_kv, ld_kv, kt, bf) &&
-                 tc::make_map_2d(&mv, v, kv_rows, ld_kv, ld_kv, kt, bf),
-             "attention_tc: cuTensorMapEncodeTiled failed");
   tc::AttnParams p = {out, ld_out, hd, q_len, n_heads, n_heads / n_kv_heads, q_col0, k_col0, v_col0, hd_stride,
                       kv_batch_rows, page_table, pt_stride, kv_len, kv_len_const, kv_len_add, scale, scale_mode, 0.f};
   int ex = 0;
   if (scale_mode == 1 && frexpf(scale, &ex) == 0.5f) p.scale_mul = 1.0f / scale;  // x / 2^k == x * 2^-k exactly
   cudaStream_t st = (cudaStream_t)stream;
-  static const int oneshot = env_int("PG_ATTN_ONESHOT", 0);  // measured slower than the tiled kernel at 2 CTAs/SM (29.5 vs 34.4 ms, batch 64)
-  if (oneshot && hdp == 128 && !page_table && !kv_len && kv_len_const <= 256 && k == v) {
-    CUtensorMap mkv;
-    PG_REQUIRE(tc::make_map_2d(&mkv, k, kv_rows, ld_kv, ld_kv, 256, bf), "attention_tc: cuTensorMapEncodeTiled failed");
-    return bf ? tc::launch_attn_oneshot<bf16>(mq, mkv, p, B, st) : tc::launch_attn_oneshot<f16>(mq, mkv, p, B, st);
+  // SigLIP-shaped problems: all keys at once, real head columns only (see attention_vit_kernel)
+  static const int vit = env_int("PG_ATTN_VIT", 1);
+  const int hd16 = ((hd + 15) / 16) * 16;
+  if (vit && hd <= 80 && (hd == hd16 || hd_stride >= hd16) && !page_table && !kv_len && kv_len_const >= 1 &&
+      kv_len_const <= tc::VIT_TK && q == k && k == v && ld_q == ld_kv && q_rows == kv_rows &&
+      (scale_mode == 0 || p.scale_mul != 0.f)) {
+    CUtensorMap m64, m16;
+    PG_REQUIRE(tc::make_map_2d_ex(&m64, q, q_rows, ld_q, ld_q, 64, tc::AQ, 128, bf) &&
+                   tc::make_map_2d_ex(&m16, q, q_rows, ld_q, ld_q, 16, tc::AQ, 32, bf),
+               "attention_tc(vit): cuTensorMapEncodeTiled failed");
+    return bf ? tc::launch_attn_vit<bf16>(m64, m16, p, B, st) : tc::launch_attn_vit<f16>(m64, m16, p, B, st);
   }
+  CUtensorMap mq, mk, mv;
+  PG_REQUIRE(tc::make_map_2d(&mq, q, q_rows, ld_q, ld_q, tc::AQ, bf) && tc::make_map_2d(&mk, k, kv_rows, ld_kv, ld_kv, kt, bf) &&
+                 tc::make_map_2d(&mv, v, kv_rows, ld_kv, ld_kv, kt, bf),
+             "attention_tc: cuTensorMapEncodeTiled failed");
+  PG_REQUIRE(hd == hdp || hd_stride >= ((hd + 63) / 64) * 64 || n_heads == 1, "attention_tc: head rows must be padded to a multiple of 64 columns");
   if (hdp == 128) return bf ? tc::launch_attn<bf16, 128, 64>(mq, mk, mv, p, B, st) : tc::launch_attn<f16, 128, 64>(mq, mk, mv, p, B, st);
   return bf ? tc::launch_attn<bf16, 256, 64>(mq, mk, mv, p, B, st) : tc::launch_attn<f16, 256, 64>(mq, mk, mv, p, B, st);
 }

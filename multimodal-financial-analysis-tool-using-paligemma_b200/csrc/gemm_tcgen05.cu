@@ -224,18 +224,25 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-bool make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows,
-                 bool is_bf16) {
+bool make_map_2d_ex(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                    int box_rows, int swizzle_bytes, bool is_bf16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+bool make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                 bool is_bf16) {
+  return make_map_2d_ex(map, base, rows, cols, ld, 64, box_rows, 128, is_bf16);
 }
 
 template <typename T, int EPI, int BN, int CL = 1>

@@ -110,6 +110,9 @@ EncodeTiledFn encode_fn();
 // 2-D row-major [rows, cols] 16-bit tensor, box = 64 columns x box_rows rows, 128-byte swizzle, zero OOB fill.
 bool make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows,
                  bool is_bf16);
+// same with an explicit box width (elements) and swizzle span (32 / 64 / 128 bytes; box_cols * 2 <= swizzle_bytes)
+bool make_map_2d_ex(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                    int box_rows, int swizzle_bytes, bool is_bf16);
 
 }  // namespace tc
 }  // namespace pg

@@ -138,10 +138,12 @@ class PaliGemmaEngine:
         self.gemm_impl = gemm_impl
         self.page_size = page_size
         self._vec = 4 if self.dtype == torch.float32 else 8
-        # tcgen05 attention (16-bit dtypes): SigLIP heads padded to 128 columns; Gemma needs hd 256 and 64-token pages
+        # tcgen05 attention (16-bit dtypes): SigLIP heads padded with zero columns; Gemma needs hd 256 and 64-token pages
         tc_ok = self.dtype != torch.float32 and os.environ.get("PG_ATTN_TC", "1") != "0"
         hdv = d.Hv // d.heads_v
-        self.vision_head_pad = 128
+        # the ViT attention kernel multiplies 16-column steps (72 -> 80); the tiled kernel needs 64-column blocks (-> 128)
+        vit = hdv <= 80 and d.P <= 256 and os.environ.get("PG_ATTN_VIT", "1") != "0"
+        self.vision_head_pad = ((hdv + 15) // 16) * 16 if vit else 128
         self.attn_tc_vision = tc_ok and hdv <= 128 and hdv % 8 == 0
         self.attn_tc_text = tc_ok and d.hd == 256 and page_size == 64
         if self.attn_tc_vision:
@@ -186,8 +188,8 @@ class PaliGemmaEngine:
                 for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
                     adopt(Lk + f"self_attn.{n}.weight", qkv_w[j * d.Hv:(j + 1) * d.Hv])
             if self.attn_tc_vision:
-                # head rows padded 72 -> 128 with zero weights / zero bias: the tcgen05 attention kernel
-                # reads whole 64-column blocks, and zeros contribute nothing to QK^T or PV
+                # head rows padded 72 -> 80 (or 128) with zero weights / zero bias: the tcgen05 attention kernels
+                # multiply whole 16-column steps (64-column blocks), and zeros contribute nothing to QK^T or PV
                 hdv, hp, nh = d.Hv // d.heads_v, self.vision_head_pad, d.heads_v
                 wp_ = torch.zeros((3, nh, hp, d.Hv), dtype=self.dtype, device=self.device)
                 wp_[:, :, :hdv] = qkv_w.view(3, nh, hdv, d.Hv)

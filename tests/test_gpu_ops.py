@@ -388,10 +388,12 @@ def test_gemm_tcgen05(dtype, M, N, K, epi):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("B,S,heads,hd", [(2, 256, 16, 72), (1, 16, 2, 72), (3, 64, 4, 72), (1, 300, 2, 128)])
-def test_attention_tc_siglip_padded_layout(dtype, B, S, heads, hd):
-    """tcgen05 attention on the SigLIP layout: fused [tokens, 3*heads*128] with each head padded to 128."""
-    hs = 128
+@pytest.mark.parametrize("B,S,heads,hd,hs", [(2, 256, 16, 72, 128), (1, 16, 2, 72, 128), (3, 64, 4, 72, 128), (1, 300, 2, 128, 128),
+                                              (2, 256, 16, 72, 80), (1, 16, 2, 72, 80), (3, 64, 4, 72, 80), (2, 200, 3, 72, 80),
+                                              (1, 130, 2, 64, 64), (2, 256, 2, 32, 32), (1, 300, 2, 72, 128), (2, 256, 4, 80, 80)])
+def test_attention_tc_siglip_padded_layout(dtype, B, S, heads, hd, hs):
+    """tcgen05 attention on the SigLIP layout: fused [tokens, 3*heads*hs] with each head padded to hs columns
+    (<= 256 keys and head_dim <= 80 take the ViT kernel, the rest the tiled kernel)."""
     q, k, v = (gen(B, heads, S, hd, seed=i, dtype=dtype) for i in (1, 2, 3))
     w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
     want = torch.matmul(F.softmax(w, dim=-1, dtype=torch.float32).to(dtype), v).transpose(1, 2).reshape(B * S, heads * hd)
