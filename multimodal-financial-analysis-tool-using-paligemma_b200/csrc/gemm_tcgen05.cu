@@ -299,6 +299,9 @@ bool gemm_tc_supported(int M, int N, int K, int lda, int ldw, int ldc, int epi, 
 bool gemm_tc_skinny_wanted(int M, int N, int K, int epi);
 int gemm_tc_skinny(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
                    int ldw, int ldc, int ldr, int epi, int out_f32, int dtype, cudaStream_t st);
+bool gemm_tc_2cta_wanted(int M, int N, int K, int epi);
+int gemm_tc_2cta(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
+                 int ldw, int ldc, int ldr, int res_mod, int epi, int out_f32, int dtype, cudaStream_t st);
 int gemm_tc_splitk_factor(int M, int N, int K, int epi, int* bn_out);
 int gemm_tc_splitk(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
                    int ldw, int ldc, int ldr, int res_mod, int epi, int out_f32, int dtype, int bn, int s,
@@ -318,6 +321,8 @@ int gemm_tc(void* C, const void* A, const void* W, const void* bias, const void*
     const int s = gemm_tc_splitk_factor(M, N, K, epi, &sk_bn);  // few tiles, long K: a cluster shares each tile
     if (s) return gemm_tc_splitk(C, A, W, bias, R, M, N, K, lda, ldw, ldc, ldr, res_mod, epi, out_f32, dtype, sk_bn, s, st);
   }
+  if (gemm_tc_2cta_wanted(M, N, K, epi))  // >= 2 waves of 256 x 256 tiles: CTA pairs (cta_group::2)
+    return gemm_tc_2cta(C, A, W, bias, R, M, N, K, lda, ldw, ldc, ldr, res_mod, epi, out_f32, dtype, st);
   // 64-wide N tiles when 128-wide ones would occupy well under one wave of the 148 SMs
   static const int bn_env = env_int("PG_GEMM_BN", 0);
   // and 256-wide ones (half the A-operand shared-memory traffic per FLOP) when there is work for > 2 waves
