@@ -23,6 +23,7 @@ constexpr int G2_BM = 128, G2_BN = 256, G2_BK = 64;
 constexpr int G2_STAGES = 6, G2_THREADS = 384;
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2, G2_W_BYTES = (G2_BN / 2) * G2_BK * 2;
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_W_BYTES;  // 32 KB per CTA per k-block
+constexpr int G2_EPI_WARPS = 8, G2_STG_BYTES = 32 * 128;  // per-warp epilogue staging: 32 rows x 64 16-bit columns
 
 struct Params2 {
   void* C;
@@ -63,13 +64,24 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// one output element: bias, rounding to T, GELU, residual -- the rounding points of gemm_tc_kernel / gemm_simt.cu
+template <typename T, int EPI>
+__device__ __forceinline__ float epi_apply(float x, float b, float r) {
+  if (EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES) x += b;
+  x = rnd<T>(x);
+  if (EPI == PG_EPI_BIAS_GELU) x = rnd<T>(gelu_tanh_fast(x));
+  if (EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES) x = rnd<T>(x + r);
+  return x;
+}
+
 template <typename T, int EPI>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, Params2 p) {
   constexpr uint32_t IDESC = umma_idesc(std::is_same<T, bf16>::value ? 1 : 0, 2 * G2_BM, G2_BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + G2_STAGES * G2_STAGE_BYTES;
+  const uint32_t stg_base = smem_base + G2_STAGES * G2_STAGE_BYTES;
+  const uint32_t bars = stg_base + G2_EPI_WARPS * G2_STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };                       // used in the leader CTA
   auto empty_bar = [&](int s) { return bars + 8u * (G2_STAGES + s); };        // one per CTA
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * G2_STAGES + a); };    // one per CTA
@@ -156,45 +168,106 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     float* Cf = reinterpret_cast<float*>(p.C);
     const T* bias = reinterpret_cast<const T*>(p.bias);
     const T* R = reinterpret_cast<const T*>(p.R);
+    constexpr bool HAS_BIAS = EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES;
+    constexpr bool HAS_RES = EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES;
+    uint8_t* wbuf = smem_raw + (stg_base - smem_u32(smem_raw)) + (warp - 4) * G2_STG_BYTES;
     for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
       const int n_blk = tile / m_pairs;
       const int m_blk = 2 * (tile % m_pairs) + (int)crank;
+      const int row0 = m_blk * G2_BM + q * 32;  // first row of this warp's TMEM lane quarter
+      const int m = row0 + lane;
+      const int ch_l = lane & 7, r_l = lane >> 3;  // staging <-> global mapping: 8 lanes per 128-byte row segment
+      const int nw0 = n_blk * G2_BN + half * (G2_BN / 2);
+      // residual rows of both 64-column slices are requested BEFORE waiting for the accumulator: ordinary loads
+      // queue behind ~190 KB of in-flight TMA data per SM, and this wait is where the epilogue warps idle anyway
+      uint4 r1[8];
+      if (HAS_RES && !p.out_f32) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr_ = it * 4 + r_l, mm = row0 + rr_, col = nw0 + ch_l * 8;
+          const T* rrow = R + (size_t)(p.res_mod > 0 ? (mm % p.res_mod) : mm) * p.ldr;
+          uint4 u0 = make_uint4(0, 0, 0, 0);
+          r1[it] = make_uint4(0, 0, 0, 0);
+          if (mm < p.M && col < p.N) u0 = ldg_cached(rrow + col);
+          if (mm < p.M && col + 64 < p.N) r1[it] = ldg_cached(rrow + col + 64);
+          *reinterpret_cast<uint4*>(wbuf + rr_ * 128 + ((ch_l ^ (rr_ & 7)) << 4)) = u0;
+        }
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = m_blk * G2_BM + q * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * G2_BN + half * (G2_BN / 2);
-      const int rm = p.res_mod > 0 ? (m % p.res_mod) : m;
+      if (p.out_f32) {
+        // fp32 rows (logits): direct 32-byte stores, thread <-> row
 #pragma unroll 1
-      for (int c = 0; c < G2_BN / 64; ++c) {
-        float v[32];
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld_wait();
-        const int n0 = n_blk * G2_BN + half * (G2_BN / 2) + c * 32;
-        if (m < p.M && n0 < p.N) {
+        for (int c = 0; c < G2_BN / 64; ++c) {
+          float v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = n_blk * G2_BN + half * (G2_BN / 2) + c * 32;
+          if (m < p.M && n0 < p.N) {
+            const int rm = p.res_mod > 0 ? (m % p.res_mod) : m;
 #pragma unroll
-          for (int j0 = 0; j0 < 32; j0 += 8) {
-            if (n0 + j0 >= p.N) break;  // N is a multiple of 8 (checked on the host)
-            float o[8], bb[8], rr[8];
-            if (EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES)
-              unpack<T>(ldg_cached(bias + n0 + j0), bb);
-            if (EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES) unpack<T>(ldg_cached(R + (size_t)rm * p.ldr + n0 + j0), rr);
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+              if (n0 + j0 >= p.N) break;  // N is a multiple of 8 (checked on the host)
+              float o[8], bb[8], rr[8];
+              if (HAS_BIAS) unpack<T>(ldg_cached(bias + n0 + j0), bb);
+              if (HAS_RES) unpack<T>(ldg_cached(R + (size_t)rm * p.ldr + n0 + j0), rr);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = v[j0 + j];
-              if (EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES) x += bb[j];
-              x = rnd<T>(x);
-              if (EPI == PG_EPI_BIAS_GELU) x = rnd<T>(gelu_tanh_fast(x));
-              if (EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES) x = rnd<T>(x + rr[j]);
-              o[j] = x;
-            }
-            if (p.out_f32) {
+              for (int j = 0; j < 8; ++j) o[j] = epi_apply<T, EPI>(v[j0 + j], bb[j], rr[j]);
               float4* dst = reinterpret_cast<float4*>(Cf + (size_t)m * p.ldc + n0 + j0);
               dst[0] = make_float4(o[0], o[1], o[2], o[3]);
               dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-              *reinterpret_cast<uint4*>(Ct + (size_t)m * p.ldc + n0 + j0) = pack<T>(o);
             }
           }
+        }
+      } else {
+        // 16-bit rows: 64-column slices through a per-warp staging tile so that the residual loads and the output
+        // stores are whole 128-byte row segments (4 rows per instruction) instead of 32 scattered 16-byte pieces
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int n0 = nw0 + sl * 64;
+          if (n0 >= p.N || row0 >= p.M) break;  // warp-uniform
+          if (HAS_RES && sl == 1) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr_ = it * 4 + r_l;
+              *reinterpret_cast<uint4*>(wbuf + rr_ * 128 + ((ch_l ^ (rr_ & 7)) << 4)) = r1[it];
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float v[32];
+            tmem_ld32(t_row + sl * 64 + cc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+              const int ch = cc * 4 + j0 / 8;
+              uint4* slot = reinterpret_cast<uint4*>(wbuf + lane * 128 + ((ch ^ (lane & 7)) << 4));
+              float o[8], bb[8], rr[8];
+              if (HAS_BIAS) {
+                if (n0 + ch * 8 < p.N) unpack<T>(ldg_cached(bias + n0 + ch * 8), bb);
+                else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) bb[j] = 0.f;
+                }
+              }
+              if (HAS_RES) unpack<T>(*slot, rr);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = epi_apply<T, EPI>(v[j0 + j], bb[j], rr[j]);
+              *slot = pack<T>(o);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr_ = it * 4 + r_l, mm = row0 + rr_, col = n0 + ch_l * 8;
+            if (mm < p.M && col < p.N)
+              *reinterpret_cast<uint4*>(Ct + (size_t)mm * p.ldc + col) =
+                  *reinterpret_cast<const uint4*>(wbuf + rr_ * 128 + ((ch_l ^ (rr_ & 7)) << 4));
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -214,7 +287,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 template <typename T, int EPI>
 static int launch2(const CUtensorMap& ma, const CUtensorMap& mw, const Params2& p, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)G2_STAGES * G2_STAGE_BYTES + 8 * (2 * G2_STAGES + 4) + 16;
+  const size_t smem = 1024 + (size_t)G2_STAGES * G2_STAGE_BYTES + G2_EPI_WARPS * G2_STG_BYTES + 8 * (2 * G2_STAGES + 4) + 16;
   auto kern = gemm_tc2_kernel<T, EPI>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     set_error("gemm_tc2: cannot reserve %zu B of shared memory", smem);
