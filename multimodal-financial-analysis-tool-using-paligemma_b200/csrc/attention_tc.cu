@@ -340,11 +340,15 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap map64, const __grid_con
         tmem_ld32(t_row + cb, s);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = rnd<T>(rnd<T>(s[j]) * mul);
-          const float e = __expf(x - m);
-          s[j] = (cb + j < T_len) ? e : 0.f;
-          l += s[j];
+        for (int j = 0; j < 32; j += 2) {
+          float x0 = s[j], x1 = s[j + 1];
+          rnd2<T>(x0, x1);                                     // QK^T rounded to T, scaled, rounded again
+          x0 *= mul; x1 *= mul;
+          rnd2<T>(x0, x1);
+          const float e0 = __expf(x0 - m), e1 = __expf(x1 - m);
+          s[j] = (cb + j < T_len) ? e0 : 0.f;
+          s[j + 1] = (cb + j + 1 < T_len) ? e1 : 0.f;
+          l += s[j] + s[j + 1];
         }
       } else {
 #pragma unroll

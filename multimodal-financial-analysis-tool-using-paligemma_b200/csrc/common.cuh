@@ -50,6 +50,20 @@ template <> __device__ __forceinline__ f16 from_f<f16>(float v) { return __float
 // the model dtype after every ATen op, so fused kernels round at the same points.
 template <typename T> __device__ __forceinline__ float rnd(float v) { return to_f<T>(from_f<T>(v)); }
 template <> __device__ __forceinline__ float rnd<float>(float v) { return v; }
+// Two values at once: ONE packed conversion (F2FP, ALU pipe) instead of two F2F conversions, which issue on the
+// XU pipe (16/clk/SM) next to MUFU.EX2 / MUFU.TANH -- same round-to-nearest-even results.
+template <typename T> __device__ __forceinline__ void rnd2(float& a, float& b) { a = rnd<T>(a); b = rnd<T>(b); }
+template <> __device__ __forceinline__ void rnd2<bf16>(float& a, float& b) {
+  uint32_t u;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));  // first source -> upper half
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void rnd2<f16>(float& a, float& b) {
+  const float2 f = __half22float2(__floats2half2_rn(a, b));
+  a = f.x;
+  b = f.y;
+}
 
 // ---------------------------------------------------------------- 16-byte vectors
 template <typename T> struct Vec;  // VEC elements of T in one 128-bit access

@@ -30,6 +30,7 @@ struct Params2 {
   const void* bias;
   const void* R;
   int M, N, K, ldc, ldr, res_mod, out_f32;
+  int m_major;  // tile order: consecutive tiles share the A rows (W small enough to stay in L2) or the W rows
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -72,6 +73,14 @@ __device__ __forceinline__ float epi_apply(float x, float b, float r) {
   if (EPI == PG_EPI_BIAS_GELU) x = rnd<T>(gelu_tanh_fast(x));
   if (EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES) x = rnd<T>(x + r);
   return x;
+}
+// two elements at once with packed conversions (keeps the XU pipe for MUFU.TANH)
+template <typename T, int EPI>
+__device__ __forceinline__ void epi_apply2(float& x0, float& x1, float b0, float b1, float r0, float r1) {
+  if (EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES) { x0 += b0; x1 += b1; }
+  rnd2<T>(x0, x1);
+  if (EPI == PG_EPI_BIAS_GELU) { x0 = gelu_tanh_fast(x0); x1 = gelu_tanh_fast(x1); rnd2<T>(x0, x1); }
+  if (EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES) { x0 += r0; x1 += r1; rnd2<T>(x0, x1); }
 }
 
 template <typename T, int EPI>
@@ -123,8 +132,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
-        const int n_blk = tile / m_pairs;                            // neighbouring clusters share the W tile (L2 reuse)
-        const int m_blk = 2 * (tile % m_pairs) + (int)crank;         // a ghost tile past M loads zeros, stores nothing
+        const int n_blk = p.m_major ? tile % n_tiles : tile / m_pairs;  // neighbouring clusters share A rows or W rows (L2 reuse)
+        const int m_blk = 2 * (p.m_major ? tile / n_tiles : tile % m_pairs) + (int)crank;  // a ghost tile past M loads zeros, stores nothing
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
@@ -172,8 +181,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     constexpr bool HAS_RES = EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES;
     uint8_t* wbuf = smem_raw + (stg_base - smem_u32(smem_raw)) + (warp - 4) * G2_STG_BYTES;
     for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
-      const int n_blk = tile / m_pairs;
-      const int m_blk = 2 * (tile % m_pairs) + (int)crank;
+      const int n_blk = p.m_major ? tile % n_tiles : tile / m_pairs;
+      const int m_blk = 2 * (p.m_major ? tile / n_tiles : tile % m_pairs) + (int)crank;
       const int row0 = m_blk * G2_BM + q * 32;  // first row of this warp's TMEM lane quarter
       const int m = row0 + lane;
       const int ch_l = lane & 7, r_l = lane >> 3;  // staging <-> global mapping: 8 lanes per 128-byte row segment
@@ -255,7 +264,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               }
               if (HAS_RES) unpack<T>(*slot, rr);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = epi_apply<T, EPI>(v[j0 + j], bb[j], rr[j]);
+              for (int j = 0; j < 8; j += 2) {
+                o[j] = v[j0 + j]; o[j + 1] = v[j0 + j + 1];
+                epi_apply2<T, EPI>(o[j], o[j + 1], bb[j], bb[j + 1], rr[j], rr[j + 1]);
+              }
               *slot = pack<T>(o);
             }
           }
@@ -332,7 +344,11 @@ int gemm_tc_2cta(void* C, const void* A, const void* W, const void* bias, const 
   CUtensorMap ma, mw;
   PG_REQUIRE(tc::make_map_2d(&ma, A, M, K, lda, tc::G2_BM, bf) && tc::make_map_2d(&mw, W, N, K, ldw, tc::G2_BN / 2, bf),
              "gemm_tc2: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", M, N, K, lda, ldw);
-  tc::Params2 p = {C, bias, R, M, N, K, ldc, ldr, res_mod, out_f32};
+  // A is re-read once per n-tile (n-major order) or W once per m-pair (m-major): stream the big operand once and
+  // keep the small one in L2
+  static const int order_env = env_int("PG_GEMM_2CTA_ORDER", -1);
+  const int m_major = order_env >= 0 ? order_env : ((long long)N * K * 2 <= (32ll << 20) ? 1 : 0);
+  tc::Params2 p = {C, bias, R, M, N, K, ldc, ldr, res_mod, out_f32, m_major};
 #define PG_TC2(E) return bf ? tc::launch2<bf16, E>(ma, mw, p, st) : tc::launch2<f16, E>(ma, mw, p, st)
   switch (epi) {
     case PG_EPI_NONE: PG_TC2(PG_EPI_NONE);
