@@ -161,6 +161,14 @@ int pg_step_advance(int64_t* next_ids, int64_t* history, int hist_stride, int* s
                     unsigned long long* keys, const int64_t* sampled, int32_t* kv_len,
                     int32_t* positions, int B, void* stream);
 
+/* Head of a cached decode step driven through the reference API (inference.py:56-63,
+ * modeling_gemma.py:557-559): ids_dst[b] = ids_src[b]; positions[b] = position; and the reference's
+ * "The input cannot be padded" check without a host synchronisation: *bad_flag (any device-visible int,
+ * e.g. pinned host memory) is set to 1 when one of the mask_n attention-mask elements is not 1.
+ * mask_kind: 0 int64, 1 float32, 2 int32, 3 bfloat16, 4 float16, 5 uint8/bool, 6 float64; mask may be NULL. */
+int pg_decode_inputs(int64_t* ids_dst, const int64_t* ids_src, int32_t* positions, int position,
+                     const void* mask, int mask_kind, long long mask_n, int* bad_flag, int B, void* stream);
+
 /* torch.argmax(logits, -1) over fp32 [B,V] (inference.py:68).  keys_ws: device u64[B] holding 0
  * on entry (left 0 on exit). */
 int pg_argmax(int64_t* out, const float* logits, unsigned long long* keys_ws, int B, int64_t V,

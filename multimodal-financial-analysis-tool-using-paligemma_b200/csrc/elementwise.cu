@@ -297,6 +297,39 @@ __global__ void step_advance_kernel(int64_t* next_ids, int64_t* history, int his
   if (b == 0 && step_counter) *step_counter = step + 1;
 }
 
+// One launch at the head of an API-driven decode step: token ids and positions into the graph's static buffers,
+// plus the reference's all-ones attention-mask check (modeling_gemma.py:559) reported through a flag instead of a
+// host synchronisation.
+template <typename M>
+__device__ __forceinline__ bool mask_is_one(const void* mask, long long i) {
+  return reinterpret_cast<const M*>(mask)[i] == (M)1;
+}
+__global__ void decode_inputs_kernel(int64_t* ids_dst, const int64_t* ids_src, int32_t* positions, int position,
+                                     const void* mask, int mask_kind, long long mask_n, int* bad_flag, int B) {
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    ids_dst[b] = ids_src[b];
+    positions[b] = position;
+  }
+  bool bad = false;
+  for (long long i = threadIdx.x; i < mask_n; i += blockDim.x) {
+    bool one;
+    switch (mask_kind) {
+      case 0: one = mask_is_one<int64_t>(mask, i); break;
+      case 1: one = mask_is_one<float>(mask, i); break;
+      case 2: one = mask_is_one<int32_t>(mask, i); break;
+      case 3: one = reinterpret_cast<const uint16_t*>(mask)[i] == 0x3F80u; break;  // bf16 1.0
+      case 4: one = reinterpret_cast<const uint16_t*>(mask)[i] == 0x3C00u; break;  // f16 1.0
+      case 5: one = mask_is_one<uint8_t>(mask, i); break;
+      default: one = mask_is_one<double>(mask, i); break;
+    }
+    bad |= !one;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0 && bad_flag) {
+    *bad_flag = 1;
+    __threadfence_system();
+  }
+}
+
 // ------------------------------------------------------------------ argmax over fp32 logits
 __global__ void argmax_partial_kernel(unsigned long long* keys, const float* __restrict__ logits, long long V) {
   const int b = blockIdx.y;
@@ -427,6 +460,15 @@ int pg_step_advance(int64_t* next_ids, int64_t* history, int hist_stride, int* s
   step_advance_kernel<<<1, ((B + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(
       next_ids, history, hist_stride, step_counter, keys, sampled, kv_len, positions, B);
   return check_launch("step_advance");
+}
+
+int pg_decode_inputs(int64_t* ids_dst, const int64_t* ids_src, int32_t* positions, int position, const void* mask,
+                     int mask_kind, long long mask_n, int* bad_flag, int B, void* stream) {
+  PG_REQUIRE(B > 0 && ids_dst && ids_src && positions, "decode_inputs: bad arguments");
+  PG_REQUIRE(!mask || (mask_kind >= 0 && mask_kind <= 6), "decode_inputs: unknown mask element kind %d", mask_kind);
+  decode_inputs_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ids_dst, ids_src, positions, position, mask, mask_kind,
+                                                           mask ? mask_n : 0, bad_flag, B);
+  return check_launch("decode_inputs");
 }
 
 int pg_argmax(int64_t* out, const float* logits, unsigned long long* keys, int B, int64_t V, void* stream) {

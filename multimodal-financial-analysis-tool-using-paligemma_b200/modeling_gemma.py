@@ -17,6 +17,7 @@ from torch import nn
 
 from modeling_siglip import SiglipVisionConfig, SiglipVisionModel, _EngineOnly
 from pg_b200 import _cabi as cabi
+from pg_b200._cabi import MASK_KIND
 from pg_b200.engine import PagedKV, PaliGemmaEngine
 
 
@@ -276,6 +277,8 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         self._engine: Optional[PaliGemmaEngine] = None
         self._engine_key = None
         self._engine_options = engine_options
+        self._mask_flag = None      # pinned int32 written by pg_decode_inputs when a decode-step mask is padded
+        self._mask_flag_np = None
         if init_weights:
             self._build(config)
         else:
@@ -377,7 +380,15 @@ class PaliGemmaForConditionalGeneration(nn.Module):
                 return_dict: bool = True, **kwargs):
         if attention_mask is None:
             raise ValueError("attention_mask must be provided")
-        assert bool(torch.all(attention_mask == 1)), "The input cannot be padded"
+        self._raise_deferred_mask_error()
+        # cached single-token steps check the mask on the device (pg_decode_inputs) and report it at the next call
+        # instead of paying the reference's host synchronisation (modeling_gemma.py:559) on every token
+        fast = (kv_cache is not None and input_ids is not None and inputs_embeds is None and labels is None
+                and input_ids.dim() == 2 and input_ids.shape[1] == 1 and input_ids.is_cuda
+                and input_ids.dtype == torch.int64 and kv_cache._paged is not None and kv_cache._paged.length > 0
+                and attention_mask.is_cuda and attention_mask.is_contiguous() and attention_mask.dtype in MASK_KIND)
+        if not fast:
+            assert bool(torch.all(attention_mask == 1)), "The input cannot be padded"
         if inputs_embeds is not None:
             raise NotImplementedError("inputs_embeds (PEFT) is outside the accelerated inference path")
         if input_ids is None:
@@ -389,7 +400,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         paged = None if kv_cache is None else kv_cache._bind(eng, B)
         cached = 0 if paged is None else paged.length
         if paged is not None and cached > 0 and q == 1:
-            logits = self._decode_one(eng, paged, input_ids, int(attention_mask.shape[1]))
+            logits = self._decode_one(eng, paged, input_ids, int(attention_mask.shape[1]), attention_mask if fast else None)
         else:
             feats = None
             if pixel_values is not None:
@@ -402,14 +413,32 @@ class PaliGemmaForConditionalGeneration(nn.Module):
             return out
         return (logits,)
 
-    def _decode_one(self, eng: PaliGemmaEngine, paged: PagedKV, input_ids, position: int) -> torch.Tensor:
+    def _decode_one(self, eng: PaliGemmaEngine, paged: PagedKV, input_ids, position: int,
+                    mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One cached step through the graph-captured decode kernels (vision tower skipped: a
-        single new token has no image slot to fill)."""
+        single new token has no image slot to fill).  `mask` (already known to be a
+        contiguous CUDA tensor of a supported dtype) is checked for padding by the same launch
+        that stages ids / positions; a violation raises AssertionError at the next forward()."""
         ds = eng.decode_state(paged.batch)
-        ds.ids.copy_(input_ids.reshape(-1), non_blocking=True)
-        ds.pos.fill_(position)
+        if mask is not None and input_ids.is_contiguous():
+            if self._mask_flag is None:
+                self._mask_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+                self._mask_flag_np = self._mask_flag.numpy()
+            cabi.check(cabi.lib().pg_decode_inputs(ds.ids.data_ptr(), input_ids.data_ptr(), ds.pos.data_ptr(), position,
+                                                   mask.data_ptr(), MASK_KIND[mask.dtype], mask.numel(),
+                                                   self._mask_flag.data_ptr(), paged.batch, cabi.stream()),
+                       "decode_inputs")
+        else:
+            ds.ids.copy_(input_ids.reshape(-1), non_blocking=True)
+            ds.pos.fill_(position)
         ds.run_steps(paged, 1)
         return ds.logits.clone().view(paged.batch, 1, -1)
+
+    def _raise_deferred_mask_error(self):
+        if self._mask_flag_np is not None and self._mask_flag_np[0] != 0:
+            torch.cuda.current_stream().synchronize()
+            self._mask_flag_np[0] = 0
+            raise AssertionError("The input cannot be padded (attention mask of an earlier cached decode step)")
 
     # ---- engine-native generation loop (not in the reference; used by bench.py)
     @torch.no_grad()

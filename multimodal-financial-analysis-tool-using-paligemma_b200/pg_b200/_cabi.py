@@ -17,6 +17,9 @@ EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_RES, EPI_GEGLU = 0, 1, 2, 3
 MAX_DECODE_BATCH = 8
 
 DTYPE_CODE = {torch.float32: PG_F32, torch.bfloat16: PG_BF16, torch.float16: PG_F16}
+# attention-mask element kinds understood by pg_decode_inputs
+MASK_KIND = {torch.int64: 0, torch.float32: 1, torch.int32: 2, torch.bfloat16: 3, torch.float16: 4, torch.uint8: 5,
+             torch.bool: 5, torch.float64: 6}
 
 _vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
 
@@ -45,6 +48,7 @@ SIGNATURES = {
     "pg_decode_gateup": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
     "pg_decode_lmhead": [_vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _i, _vp],
     "pg_step_advance": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "pg_decode_inputs": [_vp, _vp, _vp, _i, _vp, _i, _ll, _vp, _i, _vp],
     "pg_argmax": [_vp, _vp, _vp, _i, _ll, _vp],
     "pg_top_p_sample": [_vp, _vp, _vp, _i, _ll, _f, _f, _ull, _vp, _vp, _vp],
     "pg_allreduce_oneshot": [_vp, _vp, _i, _i, _i, _ll, _vp, _vp, _i, _vp],

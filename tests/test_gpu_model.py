@@ -176,6 +176,29 @@ def test_pad_token_and_errors(fp32_case):
         model(input_ids=ids.cuda(), pixel_values=pix.cuda(), attention_mask=m.cuda())
 
 
+def test_decode_step_mask_check_is_deferred(fp32_case):
+    """Cached single-token steps verify the all-ones mask on the device (pg_decode_inputs): same logits as the
+    oracle's cached step, and a padded decode-step mask raises the reference's AssertionError at the next call."""
+    model, cfg, g, ids, pix = fp32_case
+    kv = MG.KVCache()
+    mask = torch.ones_like(ids).cuda()
+    with torch.no_grad():
+        out = model(input_ids=ids.cuda(), pixel_values=pix.cuda(), attention_mask=mask, kv_cache=kv)
+        tok = out["logits"][:, -1].argmax(-1, keepdim=True)
+        for dtype in (torch.float32, torch.int64):
+            mask = torch.cat([mask.to(dtype), torch.ones((ids.shape[0], 1), dtype=dtype, device="cuda")], -1)
+            out = model(input_ids=tok, pixel_values=None, attention_mask=mask, kv_cache=kv)
+            tok = out["logits"][:, -1].argmax(-1, keepdim=True)
+        torch.cuda.synchronize()
+        assert model._mask_flag_np is not None and model._mask_flag_np[0] == 0
+        bad = torch.cat([mask, torch.ones((ids.shape[0], 1), dtype=mask.dtype, device="cuda")], -1)
+        bad[0, 3] = 0
+        model(input_ids=tok, pixel_values=None, attention_mask=bad, kv_cache=kv)   # checked on the device
+        torch.cuda.synchronize()
+        with pytest.raises(AssertionError):
+            model(input_ids=tok, pixel_values=None, attention_mask=torch.ones_like(bad), kv_cache=kv)
+
+
 def test_merge_method_matches_oracle(fp32_case):
     model, cfg, g, ids, pix = fp32_case
     sd = synth.synth_state_dict(cfg)
