@@ -136,6 +136,8 @@ class PaliGemmaEngine:
             raise RuntimeError(f"unsupported model dtype {self.dtype}")
         self.dt = cabi.DTYPE_CODE[self.dtype]
         self.gemm_impl = gemm_impl
+        self._op_timing = os.environ.get("PG_OP_TIMING", "0") == "1"
+        self._op_events = []
         self.page_size = page_size
         self._vec = 4 if self.dtype == torch.float32 else 8
         # tcgen05 attention (16-bit dtypes): SigLIP heads padded with zero columns; Gemma needs hd 256 and 64-token pages
@@ -281,6 +283,38 @@ class PaliGemmaEngine:
     def _new(self, *shape, dtype=None):
         return torch.empty(shape, dtype=dtype or self.dtype, device=self.device)
 
+    # ------------------------------------------------------------------ per-op timing (diagnostic: PG_OP_TIMING=1)
+    class _NoTimer:
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    class _EvTimer:
+        def __init__(self, sink, name): self.sink, self.name = sink, name
+        def __enter__(self):
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+            return self
+        def __exit__(self, *a):
+            self.e1.record()
+            self.sink.append((self.name, self.e0, self.e1))
+            return False
+
+    def _op_timer(self, name):
+        """CUDA-event bracket around one op when PG_OP_TIMING=1 (in-pipeline durations, L2 state as in the real
+        run); `op_times()` sums them per op name.  A no-op otherwise."""
+        if not self._op_timing:
+            return self._NoTimer()
+        return self._EvTimer(self._op_events, name)
+
+    def op_times(self, reset: bool = True) -> Dict[str, float]:
+        torch.cuda.synchronize()
+        out: Dict[str, float] = {}
+        for name, e0, e1 in self._op_events:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        if reset:
+            self._op_events = []
+        return out
+
     # ------------------------------------------------------------------ vision tower + projector
     def vision_features(self, pixels: torch.Tensor) -> torch.Tensor:
         """SiglipVisionModel.forward (modeling_siglip.py:236-255): (B,C,S,S) -> (B,P,Hv)."""
@@ -299,23 +333,31 @@ class PaliGemmaEngine:
         ln, qkv, att = self._new(T, d.Hv), self._new(T, qkv_cols), self._new(T, d.Hv)
         h2, mid = self._new(T, d.Hv), self._new(T, d.Iv)
         scale = float(hdv ** -0.5)
+        tm = self._op_timer
         for w in self.v_layers:
-            cabi.check(L.pg_layernorm(ptr(ln), ptr(h), ptr(w["ln1_w"]), ptr(w["ln1_b"]), T, d.Hv, d.eps_v, self.dt, st), "ln1")
-            self._gemm(qkv, ln, w["qkv_w"], w["qkv_b"], None, cabi.EPI_BIAS)
-            if self.attn_tc_vision:
-                hp = self.vision_head_pad
-                cabi.check(L.pg_attention_tc(ptr(att), d.Hv, ptr(qkv), T, qkv_cols, 0, ptr(qkv), ptr(qkv), T, qkv_cols,
-                                             d.heads_v * hp, 2 * d.heads_v * hp, hp, d.P, None, 0, 0, None, d.P, 0, B, d.P,
-                                             d.heads_v, d.heads_v, hdv, scale, 0, self.dt, st), "siglip attention (tcgen05)")
-            else:
-                cabi.check(L.pg_attention(ptr(att), d.Hv, ptr(qkv), 3 * d.Hv, qkv[:, d.Hv:].data_ptr(),
-                                          qkv[:, 2 * d.Hv:].data_ptr(), 3 * d.Hv, d.P * 3 * d.Hv, None, 0, 0,
-                                          None, d.P, 0, B, d.P, d.heads_v, d.heads_v, hdv, scale, 0, self.dt, st),
-                           "siglip attention")
-            self._gemm(h2, att, w["o_w"], w["o_b"], h, cabi.EPI_BIAS_RES)
-            cabi.check(L.pg_layernorm(ptr(ln), ptr(h2), ptr(w["ln2_w"]), ptr(w["ln2_b"]), T, d.Hv, d.eps_v, self.dt, st), "ln2")
-            self._gemm(mid, ln, w["fc1_w"], w["fc1_b"], None, cabi.EPI_BIAS_GELU)
-            self._gemm(h, mid, w["fc2_w"], w["fc2_b"], h2, cabi.EPI_BIAS_RES)
+            with tm("ln"):
+                cabi.check(L.pg_layernorm(ptr(ln), ptr(h), ptr(w["ln1_w"]), ptr(w["ln1_b"]), T, d.Hv, d.eps_v, self.dt, st), "ln1")
+            with tm("qkv"):
+                self._gemm(qkv, ln, w["qkv_w"], w["qkv_b"], None, cabi.EPI_BIAS)
+            with tm("attention"):
+                if self.attn_tc_vision:
+                    hp = self.vision_head_pad
+                    cabi.check(L.pg_attention_tc(ptr(att), d.Hv, ptr(qkv), T, qkv_cols, 0, ptr(qkv), ptr(qkv), T, qkv_cols,
+                                                 d.heads_v * hp, 2 * d.heads_v * hp, hp, d.P, None, 0, 0, None, d.P, 0, B, d.P,
+                                                 d.heads_v, d.heads_v, hdv, scale, 0, self.dt, st), "siglip attention (tcgen05)")
+                else:
+                    cabi.check(L.pg_attention(ptr(att), d.Hv, ptr(qkv), 3 * d.Hv, qkv[:, d.Hv:].data_ptr(),
+                                              qkv[:, 2 * d.Hv:].data_ptr(), 3 * d.Hv, d.P * 3 * d.Hv, None, 0, 0,
+                                              None, d.P, 0, B, d.P, d.heads_v, d.heads_v, hdv, scale, 0, self.dt, st),
+                               "siglip attention")
+            with tm("o_proj"):
+                self._gemm(h2, att, w["o_w"], w["o_b"], h, cabi.EPI_BIAS_RES)
+            with tm("ln"):
+                cabi.check(L.pg_layernorm(ptr(ln), ptr(h2), ptr(w["ln2_w"]), ptr(w["ln2_b"]), T, d.Hv, d.eps_v, self.dt, st), "ln2")
+            with tm("fc1"):
+                self._gemm(mid, ln, w["fc1_w"], w["fc1_b"], None, cabi.EPI_BIAS_GELU)
+            with tm("fc2"):
+                self._gemm(h, mid, w["fc2_w"], w["fc2_b"], h2, cabi.EPI_BIAS_RES)
         out = self._new(T, d.Hv)
         cabi.check(L.pg_layernorm(ptr(out), ptr(h), ptr(self.v_post_w), ptr(self.v_post_b), T, d.Hv, d.eps_v, self.dt, st), "post_ln")
         return out.view(B, d.P, d.Hv)

@@ -42,6 +42,10 @@ def main():
     res[f"vision_b{vb}_ms(gpu,wall)"] = (g, w)
     res[f"vision_b{vb}_img_per_s"] = round(vb / (g / 1e3), 1)
     res["vision_tflops"] = round(vb * 2.202e11 / (g / 1e3) / 1e12, 1)
+    if os.environ.get("PG_OP_TIMING", "0") == "1":
+        eng.op_times()
+        eng.encode_images(pixb)
+        res["vision_op_ms"] = {k: round(v, 3) for k, v in eng.op_times().items()}
     print(json.dumps(res))
 
 
