@@ -60,10 +60,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* p_ptr = smem_raw + (s_p - smem_u32(smem_raw));
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z, kvh = h / p.kv_group;
-  const int T_len = p.kv_len_dev ? (p.kv_len_dev[b] + p.kv_len_add) : p.kv_len_const;
-  const int n_tiles = (T_len + KT - 1) / KT;
   const int nv = ((p.hd + 15) / 16) * 16;        // PV output columns (multiple of 16)
   const int k_steps = (p.hd + 15) / 16;          // 16-wide K steps of QK^T that hold real data
 
@@ -80,6 +79,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // q / k / v, lengths and page tables come from the preceding kernels
+  const int T_len = p.kv_len_dev ? (p.kv_len_dev[b] + p.kv_len_add) : p.kv_len_const;
+  const int n_tiles = (T_len + KT - 1) / KT;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA + MMA issuer (one thread) =====================
@@ -222,6 +224,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw32(uint32_t smem_addr, uint32
          (1ull << 46) | (6ull << 61);
 }
 __device__ __forceinline__ void vit_softmax_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+constexpr float LOG2E_F = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(VIT_THREADS, 2)
@@ -242,6 +250,7 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap map64, const __grid_con
   uint8_t* p_ptr = base_ptr + OFF_P;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(base_ptr + OFF_BAR + 40);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z, kvh = h / p.kv_group;
   const int T_len = p.kv_len_const;
@@ -268,6 +277,7 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap map64, const __grid_con
     // ===================== TMA + MMA issuer (one thread) =====================
     const int row_q = b * p.q_len + qb * AQ, row_kv = (int)(b * p.kv_batch_rows);
     const int cq = p.q_col0 + h * p.hd_stride, ck = p.k_col0 + kvh * p.hd_stride, cv = p.v_col0 + kvh * p.hd_stride;
+    pdl_wait();  // q / k / v come from the preceding GEMM
     mbar_expect_tx(bar_qk, has_b1 ? 61440u : 49152u);
     tma_load_2d(s_q0, &map64, bar_qk, cq, row_q);
     tma_load_2d(s_k0, &map64, bar_qk, ck, row_kv);
@@ -309,6 +319,7 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap map64, const __grid_con
     const int col0 = hf * 128;
     const float mul = p.scale_mul != 0.f ? p.scale_mul : p.scale;  // exact power of two, or s*scale rounded to T
     float s[32];
+    pdl_wait();  // the output rows may still be read by a running predecessor
     mbar_wait(bar_s, 0);
     tc_fence_after();
     float m = -INFINITY;
@@ -330,6 +341,7 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap map64, const __grid_con
     vit_softmax_sync();
     m = fmaxf(red_m[r], red_m[128 + r]);
     m = rnd<T>(rnd<T>(m) * mul);                               // the row max after the reference's roundings
+    const float neg_m_l2 = -m * LOG2E_F;
     float l = 0.f;
     const int t_pad = ((T_len + 63) / 64) * 64;                // P columns the MMAs may touch
 #pragma unroll 1
@@ -339,17 +351,25 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap map64, const __grid_con
       if (cb < T_len) {
         tmem_ld32(t_row + cb, s);
         tmem_ld_wait();
+        // p = exp(x - m) as ex2(x * log2e - m * log2e): one FFMA + one MUFU.EX2 per element (results below 2^-126
+        // flush to zero); x = QK^T rounded to T, scaled, rounded again -- two values per packed conversion
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float x0 = s[j], x1 = s[j + 1];
-          rnd2<T>(x0, x1);                                     // QK^T rounded to T, scaled, rounded again
+          rnd2<T>(x0, x1);
           x0 *= mul; x1 *= mul;
           rnd2<T>(x0, x1);
-          const float e0 = __expf(x0 - m), e1 = __expf(x1 - m);
-          s[j] = (cb + j < T_len) ? e0 : 0.f;
-          s[j + 1] = (cb + j + 1 < T_len) ? e1 : 0.f;
-          l += s[j] + s[j + 1];
+          s[j] = ex2_ftz(fmaf(x0, LOG2E_F, neg_m_l2));
+          s[j + 1] = ex2_ftz(fmaf(x1, LOG2E_F, neg_m_l2));
         }
+        if (cb + 32 > T_len) {                                 // ragged last chunk only
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s[j] = (cb + j < T_len) ? s[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) { l0 += s[j]; l1 += s[j + 1]; }
+        l += l0 + l1;
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) s[j] = 0.f;
@@ -420,9 +440,8 @@ static int launch_attn_vit(const CUtensorMap& m64, const CUtensorMap& m16, const
     cudaGetLastError();
     return PG_ERR_CUDA;
   }
-  dim3 grid(cdiv(p.q_len, AQ), p.n_heads, B);
-  kern<<<grid, VIT_THREADS, smem, st>>>(m64, m16, p);
-  return check_launch("attention_vit");
+  const int ctas = cdiv(p.q_len, AQ) * p.n_heads * B;
+  return launch_tc("attention_vit", kern, dim3(cdiv(p.q_len, AQ), p.n_heads, B), dim3(VIT_THREADS), smem, 1, ctas <= 296, st, m64, m16, p);
 }
 
 template <typename T, int HDP, int KT>
@@ -435,9 +454,8 @@ static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUten
     cudaGetLastError();
     return PG_ERR_CUDA;
   }
-  dim3 grid(cdiv(p.q_len, AQ), p.n_heads, B);
-  kern<<<grid, 256, smem, st>>>(mq, mk, mv, p);
-  return check_launch("attention_tc");
+  const int ctas = cdiv(p.q_len, AQ) * p.n_heads * B;
+  return launch_tc("attention_tc", kern, dim3(cdiv(p.q_len, AQ), p.n_heads, B), dim3(256), smem, 1, ctas <= 296, st, mq, mk, mv, p);
 }
 
 }  // namespace tc

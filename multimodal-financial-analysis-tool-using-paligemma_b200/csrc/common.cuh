@@ -141,6 +141,47 @@ static int launch_pdl(const char* what, void (*kernel)(KArgs...), dim3 grid, dim
   return check_launch(what);
 }
 
+// Tensor-core kernels (prefill / vision chain): optional thread-block cluster + programmatic dependent launch
+// Kernels launched through this MUST execute pdl_wait() in every thread
+// that reads or writes global memory, and unconditionally in at least one thread per CTA.
+template <typename... KArgs, typename... Args>
+static int launch_tc(const char* what, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster,
+                     bool small, cudaStream_t st, Args... args) {
+  // measured (tools/prefill_profile.py): the early launch wins 4-6 % on the single-wave kernels of the batch-1
+  // vision tower and the 260-token prefill, and loses 3 % on the many-wave batch-64 kernels: PG_TC_PDL=1 (default)
+  // enables it for small launches only, 2 everywhere, 0 nowhere
+  static const int pdl_mode = env_int("PG_TC_PDL", 1);
+  const bool pdl = pdl_mode == 2 || (pdl_mode == 1 && small);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) {
+    set_error("%s launch: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PG_ERR_CUDA;
+  }
+  return check_launch(what);
+}
+
 __device__ __forceinline__ uint4 ldg_cached(const void* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }

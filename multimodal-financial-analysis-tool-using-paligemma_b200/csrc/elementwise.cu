@@ -50,6 +50,7 @@ __global__ void embed_merge_kernel(T* __restrict__ out, const int64_t* __restric
                                    const T* __restrict__ emb, const T* __restrict__ img,
                                    int n_tokens, int D, int64_t vocab, int64_t img_id, int64_t pad_id,
                                    int n_img_rows, float img_div, float normalizer, int* err_flag) {
+  pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
   constexpr int V = Vec<T>::N;
   __shared__ float red[32];
   const int t = blockIdx.x;
@@ -90,6 +91,7 @@ __global__ void embed_merge_kernel(T* __restrict__ out, const int64_t* __restric
 template <typename T, int MAXV>
 __global__ void rmsnorm_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ w,
                                int D, float eps) {
+  pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
   constexpr int V = Vec<T>::N;
   __shared__ float red[32];
   const T* xr = x + (size_t)blockIdx.x * D;
@@ -123,6 +125,7 @@ __global__ void rmsnorm_kernel(T* __restrict__ out, const T* __restrict__ x, con
 template <typename T, int MAXV>
 __global__ void layernorm_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ w,
                                  const T* __restrict__ b, int D, float eps) {
+  pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
   constexpr int V = Vec<T>::N;
   __shared__ float red[32];
   const T* xr = x + (size_t)blockIdx.x * D;
@@ -171,22 +174,28 @@ template <typename T, int MAXV, bool LAYERNORM>
 __global__ void __launch_bounds__(256)
 norm_rows_warp_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
                       int rows, int D, float eps) {
+  pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
   constexpr int V = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* xr = x + (size_t)row * D;
   T* orow = out + (size_t)row * D;
-  float f[MAXV][V];
-  float s = 0.f;
+  // the row is held as the raw 16-byte vectors (4 registers each, unpacked on the fly in every pass): ~45 registers,
+  // so 5-6 CTAs (40+ rows) per SM keep enough bytes in flight for HBM
+  uint4 raw[MAXV];
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
     const int c = (j * 32 + lane) * V;
-    if (c < D) {
-      unpack<T>(ldg_cached(xr + c), f[j]);
+    raw[j] = c < D ? ldg_cached(xr + c) : make_uint4(0, 0, 0, 0);
+  }
+  float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < V; ++i) s += LAYERNORM ? f[j][i] : f[j][i] * f[j][i];
-    }
+  for (int j = 0; j < MAXV; ++j) {
+    float f[V];
+    unpack<T>(raw[j], f);   // out-of-row vectors are zeros: they add nothing to either sum
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += LAYERNORM ? f[i] : f[i] * f[i];
   }
   s = warp_sum(s);
   float mean = 0.f, scale;
@@ -196,9 +205,12 @@ norm_rows_warp_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __r
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
       const int c = (j * 32 + lane) * V;
-      if (c < D)
+      if (c < D) {
+        float f[V];
+        unpack<T>(raw[j], f);
 #pragma unroll
-        for (int i = 0; i < V; ++i) { const float d = f[j][i] - mean; q += d * d; }
+        for (int i = 0; i < V; ++i) { const float d = f[i] - mean; q += d * d; }
+      }
     }
     scale = rsqrtf(warp_sum(q) / (float)D + eps);
   } else {
@@ -208,13 +220,14 @@ norm_rows_warp_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __r
   for (int j = 0; j < MAXV; ++j) {
     const int c = (j * 32 + lane) * V;
     if (c < D) {
-      float g[V], bb[V];
+      float f[V], g[V], bb[V];
+      unpack<T>(raw[j], f);
       unpack<T>(ldg_cached(w + c), g);
       if (LAYERNORM) unpack<T>(ldg_cached(b + c), bb);
 #pragma unroll
       for (int i = 0; i < V; ++i)
-        f[j][i] = LAYERNORM ? (f[j][i] - mean) * scale * g[i] + bb[i] : (f[j][i] * scale) * (1.0f + g[i]);
-      *reinterpret_cast<uint4*>(orow + c) = pack<T>(f[j]);
+        f[i] = LAYERNORM ? (f[i] - mean) * scale * g[i] + bb[i] : (f[i] * scale) * (1.0f + g[i]);
+      *reinterpret_cast<uint4*>(orow + c) = pack<T>(f);
     }
   }
 }
@@ -223,6 +236,7 @@ norm_rows_warp_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __r
 template <typename T>
 __global__ void im2col_kernel(T* __restrict__ out, const T* __restrict__ px, int C, int H, int W, int p,
                               int ld_out, long long total) {
+  pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
   const int G = W / p, P = (H / p) * G, Kc = C * p * p;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -249,6 +263,7 @@ __global__ void rope_append_kernel(T* __restrict__ q_out, const T* __restrict__ 
                                    const int32_t* __restrict__ page_table, int pt_stride, int page_size,
                                    const int32_t* __restrict__ slot_base, int q_len, int nq, int nkv, int hd,
                                    int max_pos) {
+  pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
   const int t = blockIdx.x, b = t / q_len, i = t % q_len;
   const int half = hd / 2;
   int pos = positions[t];
@@ -401,7 +416,10 @@ int pg_rmsnorm(void* out, const void* x, const void* w, int rows, int D, float e
   PG_DISPATCH_DTYPE(dtype, T, {
     constexpr int V = Vec<T>::N;
     PG_REQUIRE(D % V == 0 && D <= 256 * V * 4, "rmsnorm: unsupported D=%d", D);
-    if (rows >= 64 && D <= 32 * V * 8)
+    if (rows >= 64 && D <= 32 * V * 5)
+      norm_rows_warp_kernel<T, 5, false><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
+                                                                                        nullptr, rows, D, eps);
+    else if (rows >= 64 && D <= 32 * V * 8)
       norm_rows_warp_kernel<T, 8, false><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
                                                                                         nullptr, rows, D, eps);
     else
@@ -416,7 +434,10 @@ int pg_layernorm(void* out, const void* x, const void* w, const void* b, int row
   PG_DISPATCH_DTYPE(dtype, T, {
     constexpr int V = Vec<T>::N;
     PG_REQUIRE(D % V == 0 && D <= 256 * V * 4, "layernorm: unsupported D=%d", D);
-    if (rows >= 64 && D <= 32 * V * 8)
+    if (rows >= 64 && D <= 32 * V * 5)
+      norm_rows_warp_kernel<T, 5, true><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
+                                                                                       (const T*)b, rows, D, eps);
+    else if (rows >= 64 && D <= 32 * V * 8)
       norm_rows_warp_kernel<T, 8, true><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
                                                                                        (const T*)b, rows, D, eps);
     else

@@ -52,6 +52,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_slot = bars + 8u * (2 * NSTAGES + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  pdl_launch_dependents();  // the next kernel of the chain may set itself up while this one runs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles_real = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
   // CL == 2: schedule over (n_blk, m-pair); the CTA's own tile is m_blk = 2*mp + rank (a ghost tile past M loads
@@ -91,6 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      pdl_wait();  // A (and everything else) comes from the preceding kernels
       for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
         const int n_blk = tile / m_tiles;                          // neighbours share the W tile (L2 reuse)
         const int m_blk = (CL == 2) ? 2 * (tile % m_tiles) + (int)crank : tile % m_tiles;
@@ -146,6 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* Cf = reinterpret_cast<float*>(p.C);
     const T* bias = reinterpret_cast<const T*>(p.bias);
     const T* R = reinterpret_cast<const T*>(p.R);
+    pdl_wait();  // residual reads and output writes only after the predecessor has finished
     for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
       const int n_blk = tile / m_tiles;
       const int m_blk = (CL == 2) ? 2 * (tile % m_tiles) + (int)crank : tile % m_tiles;
@@ -259,30 +262,10 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p,
   }
   if (CL == 2) {
     const int pairs = cdiv(cdiv(p.M, BM), 2) * cdiv(p.N, BN);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (pairs < 74 ? pairs : 74));
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mw, p);
-    if (e != cudaSuccess) {
-      set_error("gemm_tc (2-CTA multicast) launch: %s", cudaGetErrorString(e));
-      cudaGetLastError();
-      return PG_ERR_CUDA;
-    }
-    return check_launch("gemm_tcgen05_mcast");
+    return launch_tc("gemm_tcgen05_mcast", kern, dim3(2 * (pairs < 74 ? pairs : 74)), dim3(THREADS), smem, 2, pairs <= 148, st, ma, mw, p);
   }
   const int tiles = cdiv(p.M, BM) * cdiv(p.N, BN);
-  const int grid = tiles < 148 ? tiles : 148;
-  kern<<<grid, THREADS, smem, st>>>(ma, mw, p);
-  return check_launch("gemm_tcgen05");
+  return launch_tc("gemm_tcgen05", kern, dim3(tiles < 148 ? tiles : 148), dim3(THREADS), smem, 1, tiles <= 296, st, ma, mw, p);
 }
 
 }  // namespace tc

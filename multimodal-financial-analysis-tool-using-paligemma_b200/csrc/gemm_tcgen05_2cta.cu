@@ -98,6 +98,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t tmem_slot = bars + 8u * (2 * G2_STAGES + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t crank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -131,6 +132,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      pdl_wait();  // A (and everything else) comes from the preceding kernels
       for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
         const int n_blk = p.m_major ? tile % n_tiles : tile / m_pairs;  // neighbouring clusters share A rows or W rows (L2 reuse)
         const int m_blk = 2 * (p.m_major ? tile / n_tiles : tile % m_pairs) + (int)crank;  // a ghost tile past M loads zeros, stores nothing
@@ -180,6 +182,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     constexpr bool HAS_BIAS = EPI == PG_EPI_BIAS || EPI == PG_EPI_BIAS_GELU || EPI == PG_EPI_BIAS_RES;
     constexpr bool HAS_RES = EPI == PG_EPI_BIAS_RES || EPI == PG_EPI_RES;
     uint8_t* wbuf = smem_raw + (stg_base - smem_u32(smem_raw)) + (warp - 4) * G2_STG_BYTES;
+    pdl_wait();  // residual reads and output writes only after the predecessor has finished
     for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
       const int n_blk = p.m_major ? tile % n_tiles : tile / m_pairs;
       const int m_blk = 2 * (p.m_major ? tile / n_tiles : tile % m_pairs) + (int)crank;
@@ -307,25 +310,7 @@ static int launch2(const CUtensorMap& ma, const CUtensorMap& mw, const Params2& 
     return PG_ERR_CUDA;
   }
   const int pairs = cdiv(cdiv(p.M, G2_BM), 2) * cdiv(p.N, G2_BN);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * (pairs < 74 ? pairs : 74));
-  cfg.blockDim = dim3(G2_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mw, p);
-  if (e != cudaSuccess) {
-    set_error("gemm_tc2 (cta_group::2) launch: %s", cudaGetErrorString(e));
-    cudaGetLastError();
-    return PG_ERR_CUDA;
-  }
-  return check_launch("gemm_tcgen05_2cta");
+  return launch_tc("gemm_tcgen05_2cta", kern, dim3(2 * (pairs < 74 ? pairs : 74)), dim3(G2_THREADS), smem, 2, pairs <= 148, st, ma, mw, p);
 }
 
 }  // namespace tc
