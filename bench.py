@@ -237,6 +237,44 @@ def time_dominant_kernel(eng, reps: int = 3):
     return ms, bytes_per_launch
 
 
+def batched_rows(eng, cfg, quick: bool):
+    """BASELINE.json configs[3] and [4] on one GPU, device-resident (prefill untimed, then CUDA-graph replays timed with
+    CUDA events): batch 32 x 256 greedy tokens, and batch 8 with a 320-token prefix x 1024 tokens of top-p sampling
+    (temperature 0.8, top_p 0.9: inference.py:92-93) over the paged KV cache."""
+    from pg_b200 import synth
+    rows = {}
+    for name, B, prefix_len, new_tokens, sample in (
+            ("configs[3] batch 32 x 256 tokens, greedy", 32, None, 64 if quick else 256, None),
+            ("configs[4] batch 8, 256 image + 64 prefix tokens, 1024 tokens, paged KV, top-p", 8, 64, 128 if quick else 1024,
+             (0.8, 0.9, 1234))):
+        ids = synth.synth_prompt_ids(cfg, batch=B, prefix_len=prefix_len).cuda()
+        pix = synth.synth_pixels(cfg, batch=B).cuda()
+        N = ids.shape[1]
+        kv = eng.new_kv(B)
+        try:
+            kv.reserve(N + new_tokens + 8)
+            with torch.no_grad():
+                logits = eng.text_forward(ids, eng.encode_images(pix), kv, logits="last")
+            ds = eng.decode_state(B)
+            ds.bind(kv, logits[:, -1].argmax(-1), position=N + 1)
+            ds.run_steps(kv, 4, sample=sample)          # graph capture + warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = new_tokens - 4
+            e0.record()
+            ds.run_steps(kv, n, sample=sample)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            hist = ds.history[:, :4 + n]
+            rows[name] = {"batch": B, "prompt_len": N, "timed_steps": n, "tokens_per_s": B * n / (ms / 1e3),
+                          "ms_per_step": ms / n, "context": f"{N + 4} -> {N + 4 + n}",
+                          "distinct_tokens_sampled": int(hist.unique().numel()),
+                          "sampling": "greedy" if sample is None else f"temperature {sample[0]}, top_p {sample[1]} (pg_top_p_sample)"}
+        finally:
+            kv.release()
+    return rows
+
+
 def run_ours(args, rank, world, local):
     from pg_b200 import synth, _cabi as cabi
     import modeling_gemma as MG
@@ -397,6 +435,27 @@ def run_ours(args, rank, world, local):
             tpeak, tsus = float(mp["bf16_tflops"]), float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"]))
         except Exception:
             tpeak, tsus = 1590.0, 1400.0
+        with torch.no_grad():
+            # prefill first: the batch-64 encode below runs into the power cap and would depress the clocks
+            f1 = eng.encode_images(pix_d)
+            eng.text_forward(ids_d, f1, None, logits="last")
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); eng.text_forward(ids_d, f1, None, logits="last"); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            pms = statistics.median(ts)
+            pflop = 2 * N * 1.98e9 + 4 * d.nq * N * N * d.hd * d.L + 2 * d.V * d.D
+            prefill = {"tokens": N, "ms": pms, "tflops": pflop / (pms / 1e3) / 1e12,
+                       "hbm_floor_ms": eng.weight_bytes_per_decode_step() / (peak * 1e9) * 1e3,
+                       "note": "text decoder over the 260-token prompt, last-position logits (weights read once: at the HBM/tensor ridge)"}
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); eng.encode_images(pix_d); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            v1 = statistics.median(ts)
         vb = args.vision_batch
         pixb = torch.rand(vb, 3, d.S, d.S, device="cuda") * 2 - 1
         with torch.no_grad():
@@ -412,20 +471,13 @@ def run_ours(args, rank, world, local):
             vision = {"batch": vb, "ms": vms, "images_per_s": vb / (vms / 1e3), "tflops": vb * flop_img / (vms / 1e3) / 1e12,
                       "frac_of_bf16_burst_peak": vb * flop_img / (vms / 1e3) / 1e12 / tpeak,
                       "frac_of_bf16_sustained_peak": vb * flop_img / (vms / 1e3) / 1e12 / tsus,
-                      "flop_per_image": flop_img, "peak_tflops": {"burst": tpeak, "sustained": tsus}}
-            f1 = eng.encode_images(pix_d)
-            eng.text_forward(ids_d, f1, None, logits="last")
-            torch.cuda.synchronize()
-            ts = []
-            for _ in range(5):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); eng.text_forward(ids_d, f1, None, logits="last"); e1.record(); torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            pms = statistics.median(ts)
-            pflop = 2 * N * 1.98e9 + 4 * d.nq * N * N * d.hd * d.L + 2 * d.V * d.D
-            prefill = {"tokens": N, "ms": pms, "tflops": pflop / (pms / 1e3) / 1e12,
-                       "hbm_floor_ms": eng.weight_bytes_per_decode_step() / (peak * 1e9) * 1e3,
-                       "note": "text decoder over the 260-token prompt, last-position logits (weights read once: at the HBM/tensor ridge)"}
+                      "flop_per_image": flop_img, "peak_tflops": {"burst": tpeak, "sustained": tsus},
+                      "batch1_ms": v1}
+
+    # ---------------- batched decode rows (configs[3], configs[4]) on one GPU
+    batched = None
+    if args.batched and world == 1:
+        batched = batched_rows(eng, cfg, quick=args.batched == 2)
 
     # ---------------- CPU baseline (oracle port, bounded sample)
     cpu = None
@@ -460,6 +512,7 @@ def run_ours(args, rank, world, local):
         "tensor_parallel": tp_block,
         "vision_encode": vision,
         "prefill": prefill,
+        "batched_decode": batched,
         "setup_s": {"synthetic_weights_cpu": round(t_weights, 1)},
     }
     print(json.dumps(line), flush=True)
@@ -475,6 +528,7 @@ def main():
     ap.add_argument("--kv-off-steps", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--vision-batch", type=int, default=64)
+    ap.add_argument("--batched", type=int, default=1, help="0 skip, 1 full configs[3]/[4] rows, 2 shortened")
     ap.add_argument("--parallel", default="replicas", choices=["tp", "replicas"],
                     help="N > 1: what `value` measures. replicas = one independent sequence per GPU (weak scaling, no "
                          "data-path collective); tp = ONE sequence, tensor-parallel decoder over NCCL (strong scaling). "

@@ -67,7 +67,8 @@ int pg_im2col(void* out, const void* pixels, int B, int C, int H, int W, int p, 
 /* C[M,N] = A[M,K] W[N,K]^T with a fused epilogue; fp32 accumulation.  R row index is
  * m % res_mod when res_mod > 0 (position-embedding broadcast over the batch).  out_f32 != 0
  * stores fp32 (lm_head `.float()`, modeling_gemma.py:417-418).  impl: 0 = auto, 1 = SIMT
- * (any dtype), 2 = tcgen05/TMA (bf16/f16 only).  Replaces every nn.Linear / matmul call site
+ * (any dtype), 2 = tcgen05/TMA (bf16/f16 only; picks the CTA-pair, single-CTA, skinny or split-K kernel by shape),
+ * 3 = the experimental swap-AB kernel for 128 < M <= 512.  Replaces every nn.Linear / matmul call site
  * of SURVEY.md §2.3 on the prefill and vision paths. */
 int pg_gemm(void* C, const void* A, const void* W, const void* bias, const void* R,
             int M, int N, int K, int lda, int ldw, int ldc, int ldr, int res_mod,

@@ -33,6 +33,11 @@ def main():
     vb = int(os.environ.get("VISION_BATCH", "64"))
     pixb = torch.rand(vb, 3, 224, 224, device="cuda") * 2 - 1
     res = {}
+    if os.environ.get("ONLY_PREFILL", "0") == "1":
+        feats = torch.randn(1, 256, 2048, device="cuda", dtype=torch.bfloat16)
+        res["text_prefill_260_last_ms"] = timed(lambda: eng.text_forward(ids, feats, None, logits="last"))
+        print(json.dumps(res))
+        return
     if os.environ.get("ONLY_VISION", "0") == "0":
         feats = eng.encode_images(pix1)
         res["vision_b1_ms(gpu,wall)"] = timed(lambda: eng.encode_images(pix1))
