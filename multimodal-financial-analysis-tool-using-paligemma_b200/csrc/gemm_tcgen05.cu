@@ -272,7 +272,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p,
 
 bool gemm_tc_supported(int M, int N, int K, int lda, int ldw, int ldc, int epi, int out_f32, int dtype) {
   static const int enabled = env_int("PG_TCGEN05", 1);
-  static const int min_m = env_int("PG_TCGEN05_MIN_M", 16);
+  static const int min_m = env_int("PG_TCGEN05_MIN_M", 4);
   if (!enabled || (dtype != PG_BF16 && dtype != PG_F16)) return false;
   if (M < min_m || N % 8 || K % 8 || lda % 8 || ldw % 8 || ldc % (out_f32 ? 4 : 8)) return false;
   if (epi < PG_EPI_NONE || epi > PG_EPI_GEGLU) return false;

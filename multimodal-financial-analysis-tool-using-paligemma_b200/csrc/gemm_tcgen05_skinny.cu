@@ -1,4 +1,4 @@
-// Skinny GEMM for batched decode (16 <= M <= 256 token rows, BASELINE configs[3]): out[M,N] = X[M,K] W[N,K]^T.
+// Skinny GEMM for batched decode (4 <= M <= 128 token rows, BASELINE configs[3]): out[M,N] = X[M,K] W[N,K]^T.
 // With so few rows the problem is a weight stream, so the operands are swapped: the WEIGHT tile is the 128-row
 // A operand of tcgen05.mma and the tokens are the N dimension (N_mma = M rounded up to 16).  A pipeline stage is
 // then 16 KB of weights + a few KB of activations, so 8-10 stages (~150 KB of weights) are in flight per SM —
@@ -289,7 +289,7 @@ bool gemm_tc_skinny_wanted(int M, int N, int K, int epi) {
   // owns whole weight tiles (gate/up 26.6 vs 29.0 us, lm_head 181 vs 211 us) and for q/k/v (9.9 vs 18.3 us); with a
   // residual epilogue and a K split (o_proj, down_proj: 16 tiles) the row-major split-K kernel is faster.
   static const int mode = env_int("PG_SKINNY", 1);   // 0 off, 1 where it wins, 2 everywhere it applies
-  if (!mode || M < 16 || M > 128 || N < 512 || K < 256 || epi < PG_EPI_NONE || epi > PG_EPI_GEGLU) return false;
+  if (!mode || M < 4 || M > 128 || N < 512 || K < 256 || epi < PG_EPI_NONE || epi > PG_EPI_GEGLU) return false;
   if (mode == 2) return true;
   const int n_tiles = cdiv(N, 128);
   return epi == PG_EPI_GEGLU || epi == PG_EPI_NONE || n_tiles >= 100;

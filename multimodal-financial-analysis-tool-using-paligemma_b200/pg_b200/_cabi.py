@@ -14,7 +14,10 @@ LIB_PATH = os.environ.get("PG_LIB_PATH") or os.path.join(_HERE, "libpg_b200.so")
 
 PG_F32, PG_BF16, PG_F16 = 0, 1, 2
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_RES, EPI_GEGLU = 0, 1, 2, 3, 4, 5
-MAX_DECODE_BATCH = 8
+MAX_DECODE_BATCH = 8            # rows one launch of the GEMV kernels can take
+# from this batch size on the decode step runs the tensor-core (swap-AB skinny GEMM) path: the GEMV kernels turn
+# ALU-bound as rows are added (batch 8: 4.34 ms/step vs ~2 ms), tools/kernel_sweep.py SWEEP_B=...
+BATCHED_DECODE_MIN = int(os.environ.get("PG_BATCHED_MIN", "4"))
 
 DTYPE_CODE = {torch.float32: PG_F32, torch.bfloat16: PG_BF16, torch.float16: PG_F16}
 # attention-mask element kinds understood by pg_decode_inputs

@@ -136,7 +136,12 @@ class PaliGemmaEngine:
             raise RuntimeError(f"unsupported model dtype {self.dtype}")
         self.dt = cabi.DTYPE_CODE[self.dtype]
         self.gemm_impl = gemm_impl
+        # rows from which the decode step / last-position lm_head use the tensor-core GEMMs instead of the GEMV kernels
+        # (fp32 verification mode has no tensor-core path: GEMV up to its 8-row limit)
+        self.batched_min = cabi.BATCHED_DECODE_MIN if self.dtype != torch.float32 else cabi.MAX_DECODE_BATCH + 1
         self._op_timing = os.environ.get("PG_OP_TIMING", "0") == "1"
+        self._vision_graphs_on = os.environ.get("PG_VISION_GRAPH", "1") != "0"
+        self._vision_graphs: Dict[tuple, tuple] = {}
         self._op_events = []
         self.page_size = page_size
         self._vec = 4 if self.dtype == torch.float32 else 8
@@ -371,7 +376,30 @@ class PaliGemmaEngine:
         return out.view(*feats.shape[:-1], self.proj_w.shape[0])
 
     def encode_images(self, pixels: torch.Tensor) -> torch.Tensor:
-        return self.project(self.vision_features(pixels))
+        """SigLIP tower + projector.  Small batches (the per-request / cache-off case: ~190 launches of 5-15 us) replay
+        a CUDA graph captured per batch size, so the launch gaps disappear; large batches are launch-insensitive."""
+        B = pixels.shape[0]
+        if (not self._vision_graphs_on or B > 8 or self._op_timing or pixels.device != self.device
+                or torch.cuda.is_current_stream_capturing()):
+            return self.project(self.vision_features(pixels))
+        key = (B, tuple(pixels.shape[1:]))
+        ent = self._vision_graphs.get(key)
+        if ent is None:
+            px = torch.empty(pixels.shape, dtype=self.dtype, device=self.device)
+            px.copy_(pixels)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):                   # warm-up outside the capture (module loading, smem attributes)
+                self.project(self.vision_features(px))
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.project(self.vision_features(px))
+            ent = self._vision_graphs[key] = (g, px, out)
+        g, px, out = ent
+        px.copy_(pixels)
+        g.replay()
+        return out.clone()
 
     # ------------------------------------------------------------------ text: q_len >= 1, general
     def text_forward(self, input_ids: torch.Tensor, image_features: Optional[torch.Tensor],
@@ -441,7 +469,7 @@ class PaliGemmaEngine:
                 x = x.view(B, q, d.D)[:, -1].contiguous()
             rows = x.shape[0]
             out = self._new(rows, self.V_l, dtype=torch.float32)
-            if rows <= cabi.MAX_DECODE_BATCH:
+            if rows < self.batched_min:
                 # a handful of rows: the weight-streaming lm_head kernel (final norm fused) beats a GEMM tile
                 cabi.check(L.pg_decode_lmhead(ptr(out), ptr(x), ptr(self.final_norm), ptr(self.lm_head), rows, d.D,
                                               self.V_l, d.eps, None, self.dt, st), "lm_head")
@@ -523,7 +551,7 @@ class DecodeState:
         eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
         B, dt = self.B, self.eng.dt
         cap = self.pf_cap_mb
-        if B > cabi.MAX_DECODE_BATCH and not eng.tp.active:
+        if B >= eng.batched_min and not eng.tp.active:
             return self._launch_step_batched(kv, sample, advance)
         cabi.check(L.pg_embed_merge(ptr(self.x), ptr(self.ids), ptr(eng.emb), None, B, d.D, d.V,
                                     d.image_token_index, d.pad_token_id, 0, eng.img_div, eng.normalizer,

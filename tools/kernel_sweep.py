@@ -56,7 +56,7 @@ def main():
     nl = len(eng.t_layers)
     e = 2
     res = {}
-    if B > cabi.MAX_DECODE_BATCH:   # batched step only (skinny-GEMM path)
+    if B >= eng.batched_min:   # batched step only (skinny-GEMM path)
         ds.run_steps(kv, 1)
         g = next(iter(ds.graphs.values()))
         med, mn = timeit(lambda: [g.replay() for _ in range(10)], 10)
