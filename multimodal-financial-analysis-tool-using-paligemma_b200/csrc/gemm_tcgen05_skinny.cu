@@ -63,6 +63,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   constexpr int PROW = NT + 4;
   float* part = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t crank = 0;
   if (S > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -88,18 +89,34 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer: weight tile(s) + the token block =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = tile_first; tile < n_tiles; tile += tile_stride) {
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        mbar_expect_tx(full_bar(stage), NW * W_BYTES + X_BYTES);
-        tma_load_2d(sa, &map_w, full_bar(stage), kb * SN_BK, tile * SN_BM);
-        if (DUAL) tma_load_2d(sa + W_BYTES, &map_w, full_bar(stage), kb * SN_BK, p.N + tile * SN_BM);
-        tma_load_2d(sa + NW * W_BYTES, &map_x, full_bar(stage), kb * SN_BK, 0);
-        if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
-      }
+    // flat item index i -> (tile, k block).  The first NSTAGES items' WEIGHT tiles are requested before
+    // griddepcontrol.wait: weights never depend on the preceding kernel, so ~150 KB per SM is already in flight
+    // when the predecessor's activations become visible; the token blocks follow the wait.
+    const int nk = kb1 - kb0;
+    const int my_tiles = tile_first < n_tiles ? (n_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
+    const int items = my_tiles * nk;
+    auto item_tile = [&](int i) { return tile_first + (i / nk) * tile_stride; };
+    auto item_kb = [&](int i) { return kb0 + i % nk; };
+    const int pre = items < NSTAGES ? items : NSTAGES;
+    for (int i = 0; i < pre; ++i) {                               // fresh barriers: every stage is free
+      const uint32_t sa = smem_base + i * STAGE_BYTES;
+      mbar_expect_tx(full_bar(i), NW * W_BYTES + X_BYTES);
+      tma_load_2d(sa, &map_w, full_bar(i), item_kb(i) * SN_BK, item_tile(i) * SN_BM);
+      if (DUAL) tma_load_2d(sa + W_BYTES, &map_w, full_bar(i), item_kb(i) * SN_BK, p.N + item_tile(i) * SN_BM);
+    }
+    pdl_wait();
+    for (int i = 0; i < pre; ++i)
+      tma_load_2d(smem_base + i * STAGE_BYTES + NW * W_BYTES, &map_x, full_bar(i), item_kb(i) * SN_BK, 0);
+    int stage = pre == NSTAGES ? 0 : pre;
+    uint32_t phase = pre == NSTAGES ? 1 : 0;
+    for (int i = pre; i < items; ++i) {
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      const uint32_t sa = smem_base + stage * STAGE_BYTES;
+      mbar_expect_tx(full_bar(stage), NW * W_BYTES + X_BYTES);
+      tma_load_2d(sa, &map_w, full_bar(stage), item_kb(i) * SN_BK, item_tile(i) * SN_BM);
+      if (DUAL) tma_load_2d(sa + W_BYTES, &map_w, full_bar(stage), item_kb(i) * SN_BK, p.N + item_tile(i) * SN_BM);
+      tma_load_2d(sa + NW * W_BYTES, &map_x, full_bar(stage), item_kb(i) * SN_BK, 0);
+      if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer: D^T[128 features, NT tokens] += W_tile X_tile^T =====================
@@ -136,6 +153,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   float* Cf = reinterpret_cast<float*>(p.C);
   const T* bias = reinterpret_cast<const T*>(p.bias);
   const T* R = reinterpret_cast<const T*>(p.R);
+  if (warp >= 4) pdl_wait();   // residual reads / output writes only after the predecessor has finished
   auto finish = [&](int tile, float (&v)[16], float (&u)[DUAL ? 16 : 1], int m0) {
     const int n = tile * SN_BM + r;
     if (n >= p.N) return;
@@ -244,25 +262,8 @@ static int launch_sn(const CUtensorMap& mx, const CUtensorMap& mw, const SnParam
     return PG_ERR_CUDA;
   }
   const int n_tiles = cdiv(p.N, SN_BM);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(S > 1 ? n_tiles * S : (n_tiles < 148 ? n_tiles : 148));
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = S;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = S > 1 ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mx, mw, p);
-  if (e != cudaSuccess) {
-    set_error("gemm_tc_skinny launch: %s", cudaGetErrorString(e));
-    cudaGetLastError();
-    return PG_ERR_CUDA;
-  }
-  return check_launch("gemm_tcgen05_skinny");
+  const int grid = S > 1 ? n_tiles * S : (n_tiles < 148 ? n_tiles : 148);
+  return launch_tc("gemm_tcgen05_skinny", kern, dim3(grid), dim3(256), smem, S, true, st, mx, mw, p);
 }
 
 template <typename T, int EPI, int NT>

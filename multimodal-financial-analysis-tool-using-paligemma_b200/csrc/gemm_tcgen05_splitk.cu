@@ -51,6 +51,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* part = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));  // [BN][128] fp32, reuses the stage ring
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const int tile = blockIdx.x / S;
@@ -76,6 +77,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (warp == 0 && lane == 0) {
     int stage = 0;
     uint32_t phase = 0;
+    pdl_wait();
     for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(empty_bar(stage), phase ^ 1);
       const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -104,6 +106,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
   const bool have_k = kb1 > kb0;
   if (warp >= 4) {
+    pdl_wait();               // residual reads / output writes only after the predecessor has finished
     mbar_wait(tfull_bar, 0);  // every MMA of this CTA has completed: accumulator final, stage ring idle
     tc_fence_after();
     if (rank != 0) {
@@ -183,25 +186,7 @@ static int launch_sk(const CUtensorMap& ma, const CUtensorMap& mw, const SkParam
     return PG_ERR_CUDA;
   }
   const int tiles = cdiv(p.M, SK_BM) * cdiv(p.N, BN);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tiles * S);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = S;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mw, p);
-  if (e != cudaSuccess) {
-    set_error("gemm_tc_splitk launch: %s", cudaGetErrorString(e));
-    cudaGetLastError();
-    return PG_ERR_CUDA;
-  }
-  return check_launch("gemm_tcgen05_splitk");
+  return launch_tc("gemm_tcgen05_splitk", kern, dim3(tiles * S), dim3(256), smem, S, true, st, ma, mw, p);
 }
 
 template <typename T, int EPI>
