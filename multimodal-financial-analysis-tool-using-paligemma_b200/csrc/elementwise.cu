@@ -92,6 +92,7 @@ template <typename T, int MAXV>
 __global__ void rmsnorm_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ w,
                                int D, float eps) {
   pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
+  pdl_wait();               // (launched with the PDL attribute when the grid is small: inputs come from the predecessor)
   constexpr int V = Vec<T>::N;
   __shared__ float red[32];
   const T* xr = x + (size_t)blockIdx.x * D;
@@ -126,6 +127,7 @@ template <typename T, int MAXV>
 __global__ void layernorm_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ w,
                                  const T* __restrict__ b, int D, float eps) {
   pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
+  pdl_wait();               // (launched with the PDL attribute when the grid is small: inputs come from the predecessor)
   constexpr int V = Vec<T>::N;
   __shared__ float red[32];
   const T* xr = x + (size_t)blockIdx.x * D;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(256)
 norm_rows_warp_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
                       int rows, int D, float eps) {
   pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
+  pdl_wait();               // (launched with the PDL attribute when the grid is small: inputs come from the predecessor)
   constexpr int V = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -264,6 +267,7 @@ __global__ void rope_append_kernel(T* __restrict__ q_out, const T* __restrict__ 
                                    const int32_t* __restrict__ slot_base, int q_len, int nq, int nkv, int hd,
                                    int max_pos) {
   pdl_launch_dependents();  // a tensor-core kernel launched next may start its prologue now
+  pdl_wait();               // (launched with the PDL attribute when the grid is small: inputs come from the predecessor)
   const int t = blockIdx.x, b = t / q_len, i = t % q_len;
   const int half = hd / 2;
   int pos = positions[t];
@@ -416,16 +420,17 @@ int pg_rmsnorm(void* out, const void* x, const void* w, int rows, int D, float e
   PG_DISPATCH_DTYPE(dtype, T, {
     constexpr int V = Vec<T>::N;
     PG_REQUIRE(D % V == 0 && D <= 256 * V * 4, "rmsnorm: unsupported D=%d", D);
+    const T* none = nullptr;
     if (rows >= 64 && D <= 32 * V * 5)
-      norm_rows_warp_kernel<T, 5, false><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
-                                                                                        nullptr, rows, D, eps);
-    else if (rows >= 64 && D <= 32 * V * 8)
-      norm_rows_warp_kernel<T, 8, false><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
-                                                                                        nullptr, rows, D, eps);
-    else
-      rmsnorm_kernel<T, 4><<<rows, 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w, D, eps);
+      return launch_tc("rmsnorm", norm_rows_warp_kernel<T, 5, false>, dim3(cdiv(rows, 8)), dim3(256), 0, 1, rows <= 4096,
+                       (cudaStream_t)stream, (T*)out, (const T*)x, (const T*)w, none, rows, D, eps);
+    if (rows >= 64 && D <= 32 * V * 8)
+      return launch_tc("rmsnorm", norm_rows_warp_kernel<T, 8, false>, dim3(cdiv(rows, 8)), dim3(256), 0, 1, rows <= 4096,
+                       (cudaStream_t)stream, (T*)out, (const T*)x, (const T*)w, none, rows, D, eps);
+    return launch_tc("rmsnorm", rmsnorm_kernel<T, 4>, dim3(rows), dim3(256), 0, 1, rows <= 1024, (cudaStream_t)stream, (T*)out,
+                     (const T*)x, (const T*)w, D, eps);
   });
-  return check_launch("rmsnorm");
+  return PG_OK;
 }
 
 int pg_layernorm(void* out, const void* x, const void* w, const void* b, int rows, int D, float eps,
@@ -435,16 +440,15 @@ int pg_layernorm(void* out, const void* x, const void* w, const void* b, int row
     constexpr int V = Vec<T>::N;
     PG_REQUIRE(D % V == 0 && D <= 256 * V * 4, "layernorm: unsupported D=%d", D);
     if (rows >= 64 && D <= 32 * V * 5)
-      norm_rows_warp_kernel<T, 5, true><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
-                                                                                       (const T*)b, rows, D, eps);
-    else if (rows >= 64 && D <= 32 * V * 8)
-      norm_rows_warp_kernel<T, 8, true><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
-                                                                                       (const T*)b, rows, D, eps);
-    else
-      layernorm_kernel<T, 4><<<rows, 256, 0, (cudaStream_t)stream>>>((T*)out, (const T*)x, (const T*)w,
-                                                                     (const T*)b, D, eps);
+      return launch_tc("layernorm", norm_rows_warp_kernel<T, 5, true>, dim3(cdiv(rows, 8)), dim3(256), 0, 1, rows <= 4096,
+                       (cudaStream_t)stream, (T*)out, (const T*)x, (const T*)w, (const T*)b, rows, D, eps);
+    if (rows >= 64 && D <= 32 * V * 8)
+      return launch_tc("layernorm", norm_rows_warp_kernel<T, 8, true>, dim3(cdiv(rows, 8)), dim3(256), 0, 1, rows <= 4096,
+                       (cudaStream_t)stream, (T*)out, (const T*)x, (const T*)w, (const T*)b, rows, D, eps);
+    return launch_tc("layernorm", layernorm_kernel<T, 4>, dim3(rows), dim3(256), 0, 1, rows <= 1024, (cudaStream_t)stream,
+                     (T*)out, (const T*)x, (const T*)w, (const T*)b, D, eps);
   });
-  return check_launch("layernorm");
+  return PG_OK;
 }
 
 int pg_im2col(void* out, const void* pixels, int B, int C, int H, int W, int p, int ld_out, int dtype,
@@ -467,11 +471,11 @@ int pg_rope_append(void* q_out, const void* qkv, const float* inv_freq, const in
   if (B * q_len <= 0) return PG_OK;
   PG_REQUIRE(hd % 2 == 0, "rope_append: odd head_dim");
   PG_DISPATCH_DTYPE(dtype, T, {
-    rope_append_kernel<T><<<B * q_len, 256, 0, (cudaStream_t)stream>>>(
-        (T*)q_out, (const T*)qkv, inv_freq, positions, (T*)k_pool, (T*)v_pool, page_table, pt_stride,
-        page_size, slot_base, q_len, nq, nkv, hd, max_pos);
+    return launch_tc("rope_append", rope_append_kernel<T>, dim3(B * q_len), dim3(256), 0, 1, B * q_len <= 1024,
+                     (cudaStream_t)stream, (T*)q_out, (const T*)qkv, inv_freq, positions, (T*)k_pool, (T*)v_pool, page_table,
+                     pt_stride, page_size, slot_base, q_len, nq, nkv, hd, max_pos);
   });
-  return check_launch("rope_append");
+  return PG_OK;
 }
 
 int pg_step_advance(int64_t* next_ids, int64_t* history, int hist_stride, int* step_counter,
