@@ -53,10 +53,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_q = base, s_k = s_q + Q_BYTES, s_v = s_k + K_BYTES, s_p = s_v + V_BYTES;
+  // K/V tiles are double-buffered: tile it+1 is requested as soon as S(it) has been issued, so its TMA latency hides
+  // behind the softmax of tile it instead of heading every step of the chain
+  const uint32_t s_q = base, s_kv = s_q + Q_BYTES, s_p = s_kv + 2 * (K_BYTES + V_BYTES);
+  auto s_k = [&](int bf) { return s_kv + bf * (K_BYTES + V_BYTES); };
+  auto s_v = [&](int bf) { return s_kv + bf * (K_BYTES + V_BYTES) + K_BYTES; };
   const uint32_t bars = s_p + P_BYTES;
-  const uint32_t bar_q = bars, bar_kv = bars + 8, bar_s = bars + 16, bar_sfree = bars + 24, bar_p = bars + 32,
-                 bar_o = bars + 40, tmem_slot = bars + 48;
+  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 16, bar_sfree = bars + 24, bar_p = bars + 32,
+                 bar_o = bars + 40, bar_kv1 = bars + 48, tmem_slot = bars + 56;
+  auto bar_kv = [&](int bf) { return bf ? bar_kv1 : bar_kv0; };
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* p_ptr = smem_raw + (s_p - smem_u32(smem_raw));
 
@@ -67,7 +72,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int k_steps = (p.hd + 15) / 16;          // 16-wide K steps of QK^T that hold real data
 
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_sfree, 128);
+    mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv1, 1); mbar_init(bar_s, 1); mbar_init(bar_sfree, 128);
     mbar_init(bar_p, 128); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -90,37 +95,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     mbar_expect_tx(bar_q, Q_BYTES);
     for (int kb = 0; kb < KB; ++kb)
       tma_load_2d(s_q + kb * (AQ * 128), &map_q, bar_q, p.q_col0 + h * p.hd_stride + kb * 64, b * p.q_len + qb * AQ);
-    mbar_wait(bar_q, 0);
-    int it = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int t = 0; t < n_tiles; ++t, ++it) {
-        if (it > 0) mbar_wait(bar_sfree, (it - 1) & 1);            // S of the previous tile has been read
-        if (pass == 1 && t > 0) mbar_wait(bar_o, (t - 1) & 1);     // previous PV finished with V and P
-        const int row = p.page_table ? p.page_table[(size_t)b * p.pt_stride + t] * KT
-                                     : (int)(b * p.kv_batch_rows) + t * KT;
-        mbar_expect_tx(bar_kv, pass == 1 ? K_BYTES + V_BYTES : K_BYTES);
+    // request K (and V in pass 1) of flat step i into buffer i & 1
+    const int total = 2 * n_tiles;
+    auto request = [&](int i) {
+      const int pass = i >= n_tiles ? 1 : 0, t = pass ? i - n_tiles : i, bf = i & 1;
+      const int row = p.page_table ? p.page_table[(size_t)b * p.pt_stride + t] * KT
+                                   : (int)(b * p.kv_batch_rows) + t * KT;
+      mbar_expect_tx(bar_kv(bf), pass == 1 ? K_BYTES + V_BYTES : K_BYTES);
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_2d(s_k(bf) + kb * (KT * 128), &map_k, bar_kv(bf), p.k_col0 + kvh * p.hd_stride + kb * 64, row);
+      if (pass == 1)
         for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(s_k + kb * (KT * 128), &map_k, bar_kv, p.k_col0 + kvh * p.hd_stride + kb * 64, row);
-        if (pass == 1)
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_2d(s_v + kb * (KT * 128), &map_v, bar_kv, p.v_col0 + kvh * p.hd_stride + kb * 64, row);
-        mbar_wait(bar_kv, it & 1);
+          tma_load_2d(s_v(bf) + kb * (KT * 128), &map_v, bar_kv(bf), p.v_col0 + kvh * p.hd_stride + kb * 64, row);
+    };
+    if (total > 0) request(0);
+    mbar_wait(bar_q, 0);
+    for (int it = 0; it < total; ++it) {
+      const int pass = it >= n_tiles ? 1 : 0, t = pass ? it - n_tiles : it, bf = it & 1;
+      if (it > 0) mbar_wait(bar_sfree, (it - 1) & 1);            // S of the previous tile has been read
+      if (pass == 1 && t > 0) mbar_wait(bar_o, (t - 1) & 1);     // previous PV finished with V and P
+      mbar_wait(bar_kv(bf), (it >> 1) & 1);
+      tc_fence_after();
+      for (int ks = 0; ks < k_steps; ++ks) {                     // S = Q K^T
+        const uint32_t off_q = (ks / 4) * (AQ * 128) + (ks % 4) * 32, off_k = (ks / 4) * (KT * 128) + (ks % 4) * 32;
+        umma(tmem_base + S_COL, umma_desc(s_q + off_q), umma_desc(s_k(bf) + off_k), idesc_s, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+      // the other buffer held step it-1: its K was consumed by S(it-1) (complete: bar_sfree above), its V by PV(it-1)
+      // (complete: bar_o above) -- free for step it+1
+      if (it + 1 < total) request(it + 1);
+      if (pass == 1) {
+        mbar_wait(bar_p, t & 1);                                 // P tile is in shared memory
         tc_fence_after();
-        for (int ks = 0; ks < k_steps; ++ks) {                     // S = Q K^T
-          const uint32_t off_q = (ks / 4) * (AQ * 128) + (ks % 4) * 32, off_k = (ks / 4) * (KT * 128) + (ks % 4) * 32;
-          umma(tmem_base + S_COL, umma_desc(s_q + off_q), umma_desc(s_k + off_k), idesc_s, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < KT / 16; ++ks) {                   // O += P V
+          const uint32_t off_p = (ks / 4) * (AQ * 128) + (ks % 4) * 32;
+          umma(tmem_base + O_COL, umma_desc(s_p + off_p), umma_desc_mn(s_v(bf) + ks * 2048, KT * 128), idesc_o,
+               (t > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit(bar_s);
-        if (pass == 1) {
-          mbar_wait(bar_p, t & 1);                                 // P tile is in shared memory
-          tc_fence_after();
-          for (int ks = 0; ks < KT / 16; ++ks) {                   // O += P V
-            const uint32_t off_p = (ks / 4) * (AQ * 128) + (ks % 4) * 32;
-            umma(tmem_base + O_COL, umma_desc(s_p + off_p), umma_desc_mn(s_v + ks * 2048, KT * 128), idesc_o,
-                 (t > 0 || ks > 0) ? 1u : 0u);
-          }
-          umma_commit(bar_o);
-        }
+        umma_commit(bar_o);
       }
     }
   } else if (warp >= 4) {
@@ -447,7 +459,7 @@ static int launch_attn_vit(const CUtensorMap& m64, const CUtensorMap& m16, const
 template <typename T, int HDP, int KT>
 static int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int B,
                        cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)(AQ * HDP * 2) + 2 * (size_t)(KT * HDP * 2) + (size_t)(AQ * KT * 2) + 64;
+  const size_t smem = 1024 + (size_t)(AQ * HDP * 2) + 4 * (size_t)(KT * HDP * 2) + (size_t)(AQ * KT * 2) + 64;
   auto kern = attention_tc_kernel<T, HDP, KT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     set_error("attention_tc: cannot reserve %zu B of shared memory", smem);
