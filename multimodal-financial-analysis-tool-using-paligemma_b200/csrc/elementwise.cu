@@ -277,21 +277,24 @@ __global__ void rope_append_kernel(T* __restrict__ q_out, const T* __restrict__ 
   const size_t kv_row = ((size_t)page * page_size + (slot % page_size)) * (size_t)(nkv * hd);
   const T* row = qkv + (size_t)t * (nq + 2 * nkv) * hd;
   T* qo = q_out + (size_t)t * nq * hd;
-  const int n_rot = (nq + nkv) * half;
-  for (int u = threadIdx.x; u < n_rot; u += blockDim.x) {
-    const int h = u / half, j = u % half;
+  // a thread owns one rotation index j (cos / sin evaluated once, reused for every head) and every other head
+  const int jl = threadIdx.x % (blockDim.x / 2), hg = threadIdx.x / (blockDim.x / 2);
+  for (int j = jl; j < half; j += blockDim.x / 2) {
     const float ang = (float)pos * inv_freq[j];
     const float c = rnd<T>(cosf(ang)), s = rnd<T>(sinf(ang));
-    const float x1 = to_f<T>(row[h * hd + j]), x2 = to_f<T>(row[h * hd + j + half]);
-    const float o1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(-x2 * s));
-    const float o2 = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
-    if (h < nq) {
-      qo[h * hd + j] = from_f<T>(o1);
-      qo[h * hd + j + half] = from_f<T>(o2);
-    } else {
-      const int kh = h - nq;
-      k_pool[kv_row + kh * hd + j] = from_f<T>(o1);
-      k_pool[kv_row + kh * hd + j + half] = from_f<T>(o2);
+#pragma unroll 3
+    for (int h = hg; h < nq + nkv; h += 2) {
+      const float x1 = to_f<T>(row[h * hd + j]), x2 = to_f<T>(row[h * hd + j + half]);
+      const float o1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(-x2 * s));
+      const float o2 = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
+      if (h < nq) {
+        qo[h * hd + j] = from_f<T>(o1);
+        qo[h * hd + j + half] = from_f<T>(o2);
+      } else {
+        const int kh = h - nq;
+        k_pool[kv_row + kh * hd + j] = from_f<T>(o1);
+        k_pool[kv_row + kh * hd + j + half] = from_f<T>(o2);
+      }
     }
   }
   const T* vrow = row + (size_t)(nq + nkv) * hd;
