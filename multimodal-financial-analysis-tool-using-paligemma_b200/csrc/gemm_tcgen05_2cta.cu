@@ -87,6 +87,8 @@ template <typename T, int EPI>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, Params2 p) {
   constexpr uint32_t IDESC = umma_idesc(std::is_same<T, bf16>::value ? 1 : 0, 2 * G2_BM, G2_BN);
+  // a last n-tile with <= 128 real columns (N = 1152: o_proj, fc2) runs N = 128 MMAs: each CTA supplies 64 W rows
+  constexpr uint32_t IDESC_HALF = umma_idesc(std::is_same<T, bf16>::value ? 1 : 0, 2 * G2_BM, G2_BN / 2);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + G2_STAGES * G2_STAGE_BYTES;
@@ -136,13 +138,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int tile = sched_first; tile < total_tiles; tile += sched_stride) {
         const int n_blk = p.m_major ? tile % n_tiles : tile / m_pairs;  // neighbouring clusters share A rows or W rows (L2 reuse)
         const int m_blk = 2 * (p.m_major ? tile / n_tiles : tile % m_pairs) + (int)crank;  // a ghost tile past M loads zeros, stores nothing
+        const int w_step = (n_blk * G2_BN + G2_BN / 2 >= p.N) ? G2_BN / 4 : G2_BN / 2;  // half tile: 64 rows per CTA
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
           const uint32_t full_leader = mapa_u32(full_bar(stage), 0);
           if (leader) mbar_expect_tx(full_bar(stage), 2 * G2_STAGE_BYTES);  // both CTAs' bytes
           tma_load_2d_cg2(sa, &map_a, full_leader, kb * G2_BK, m_blk * G2_BM);
-          tma_load_2d_cg2(sa + G2_A_BYTES, &map_w, full_leader, kb * G2_BK, n_blk * G2_BN + (int)crank * (G2_BN / 2));
+          tma_load_2d_cg2(sa + G2_A_BYTES, &map_w, full_leader, kb * G2_BK, n_blk * G2_BN + (int)crank * w_step);
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -156,13 +159,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BN;
+        const int n_blk_mma = p.m_major ? tile % n_tiles : tile / m_pairs;
+        const uint32_t idesc = (n_blk_mma * G2_BN + G2_BN / 2 >= p.N) ? IDESC_HALF : IDESC;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < G2_BK / 16; ++k)
-            umma_cg2(d_tmem, umma_desc(sa + k * 32), umma_desc(sa + G2_A_BYTES + k * 32), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_cg2(d_tmem, umma_desc(sa + k * 32), umma_desc(sa + G2_A_BYTES + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit_cg2(empty_bar(stage), (uint16_t)0x3);  // the stage is free in BOTH CTAs once these MMAs have read it
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
