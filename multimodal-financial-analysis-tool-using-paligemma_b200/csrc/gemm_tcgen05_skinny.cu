@@ -293,7 +293,8 @@ bool gemm_tc_skinny_wanted(int M, int N, int K, int epi) {
   if (!mode || M < 4 || M > 128 || N < 512 || K < 256 || epi < PG_EPI_NONE || epi > PG_EPI_GEGLU) return false;
   if (mode == 2) return true;
   const int n_tiles = cdiv(N, 128);
-  return epi == PG_EPI_GEGLU || epi == PG_EPI_NONE || n_tiles >= 100;
+  // up to 8 rows the swap-AB stream also wins for the residual projections (batch 8 step: 1.92 vs 2.00 ms)
+  return epi == PG_EPI_GEGLU || epi == PG_EPI_NONE || n_tiles >= 100 || M <= 8;
 }
 
 int gemm_tc_skinny(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
