@@ -186,6 +186,13 @@ def run_reference(args, rank, world):
     reference is Python and does not travel to the GPU box), all host threads, same workload."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses every core the process may run on
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     from pg_b200 import synth
     cfg = synth.CONFIGS[MODEL]
     sd, _ = build_weights_cpu(cfg)
