@@ -58,6 +58,18 @@ int pg_rmsnorm(void* out, const void* x, const void* w, int rows, int D, float e
 int pg_layernorm(void* out, const void* x, const void* w, const void* b, int rows, int D,
                  float eps, int dtype, void* stream);
 
+/* Image pre-processing on the device (processing_paligemma.py:13-50).  pg_resample_u8 is one pass of Pillow's 8-bit
+ * bicubic resize (Image.resize(..., BICUBIC), libImaging/Resample.c) along one axis of an interleaved uint8 image:
+ * vertical == 0: in (rows, n_in, C) -> out (rows, n_out, C); vertical != 0: in (n_in, rows, C) -> out (n_out, rows, C).
+ * bounds int32 [n_out][2] = (first input index, tap count), kk int32 [n_out][ksize] = 22-bit fixed-point taps, both
+ * from the host (pg_b200/preprocess.py::resample_coeffs).  Horizontal pass first, then vertical, as Pillow does.
+ * pg_u8_to_chw: out[c][y][x] = lut[in[y][x][c]] in the model dtype; lut float32 [256] = ((b/255) - mean) / std with
+ * the reference's dtypes (pg_b200/preprocess.py::value_table). */
+int pg_resample_u8(uint8_t* out, const uint8_t* in, const int32_t* bounds, const int32_t* kk, int ksize,
+                   int rows, int n_in, int n_out, int channels, int vertical, void* stream);
+int pg_u8_to_chw(void* out, const uint8_t* in, const float* lut, int H, int W, int channels, int dtype,
+                 void* stream);
+
 /* SiglipVisionEmbeddings patch conv as im2col (modeling_siglip.py:45-51,67-73): stride == kernel
  * so it is a pure permutation: out[(b*P + py*G + px), c*p*p + ky*p + kx], row stride ld_out
  * (columns beyond C*p*p are zero-filled up to ld_out). */
