@@ -230,7 +230,7 @@ def time_dominant_kernel(eng, reps: int = 3):
     def sweep():
         for w in eng.t_layers:
             cabi.check(L.pg_decode_gateup(out.data_ptr(), x.data_ptr(), w["ln2"].data_ptr(), w["gu"].data_ptr(), 1,
-                                          d.D, F_l, d.eps, eng.dt, st))
+                                          d.D, F_l, d.eps, None, None, eng.dt, st))
     sweep()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

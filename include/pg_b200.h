@@ -34,6 +34,23 @@ enum {
   PG_EPI_GEGLU = 5      /* C = gelu_tanh(A Wg^T) * (A Wu^T), W = [Wg; Wu]  GemmaMLP */
 };
 
+/* One exchange of the tensor-parallel decoder over NVLink peer memory (csrc/tp_exchange.cuh; SURVEY.md §8e: the
+ * reference is single-device, the sharding is the north star's).  The PRODUCER kernel stores this rank's fp32 partial
+ * as {value, sequence number} words into slot (parity, rank) of EVERY rank's buffer; the CONSUMER kernel waits for all
+ * `size` slots of its local buffer and sums them in rank order.  Passed by pointer (host memory, read at launch);
+ * NULL means "not tensor parallel" everywhere a parameter of this type appears. */
+typedef struct pg_tp_exchange {
+  const void* peers;    /* device array of `size` pointers: base address of every rank's exchange buffer        */
+  const int* epoch;     /* device int: decode-step counter of this rank, advanced by pg_tp_begin_step           */
+  int* err_dev;         /* device int: set when a wait timed out (lost peer); later waits return at once         */
+  int* err_host;        /* pinned host int mirrored from err_dev (may be NULL)                                   */
+  long long region_off; /* byte offset of this exchange's region inside the buffers                              */
+  long long slot_bytes; /* bytes of one (parity, source rank) slot: 8 per fp32 word                              */
+  int rank, size;       /* this rank, number of ranks (2..8)                                                     */
+  int index, stride;    /* sequence number = *epoch * stride + index, 1 <= index < stride; exchanges that follow  */
+                        /* one another in the same region must alternate the parity of `index`                   */
+} pg_tp_exchange;
+
 const char* pg_last_error(void);
 int pg_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
@@ -135,8 +152,12 @@ int pg_set_next_prefetch(const void* ptr, long long bytes);
 int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_qkv,
                   const float* inv_freq, const int32_t* positions, void* k_pool, void* v_pool,
                   const int32_t* page_table, int pt_stride, int page_size, const int32_t* kv_len,
-                  int B, int D, int nq, int nkv, int hd, float eps, int max_pos, int dtype,
-                  void* stream);
+                  int B, int D, int nq, int nkv, int hd, float eps, int max_pos,
+                  const pg_tp_exchange* ex, void* x_out, int dtype, void* stream);
+/* ex != NULL (tensor parallel; same meaning in pg_decode_gateup / pg_decode_lmhead): the residual stream this
+ * kernel normalises is x_new = rnd(x + rnd(sum over ranks of the fp32 partials of exchange `ex`)), i.e. the
+ * all-reduce of the previous o_proj / down_proj and the `residual + hidden_states` of modeling_gemma.py:327,336
+ * happen in this kernel's prologue; x_new is also written to x_out [B,D] (must not alias x). */
 
 /* split-K MQA attention over the paged cache for one new token per sequence
  * (modeling_gemma.py:262-288).  Attends kv_len[b]+kv_len_add entries.  ws: fp32 workspace of
@@ -149,14 +170,16 @@ int pg_decode_attention(void* out, const void* q, const void* k_pool, const void
                         void* stream);
 
 /* out[B,N] = (x[B,K] W[N,K]^T) + R  — o_proj / down_proj with the residual add
- * (modeling_gemma.py:291,327 and :134,336).  R may be NULL. */
+ * (modeling_gemma.py:291,327 and :134,336).  R may be NULL.  ex != NULL (tensor parallel: W holds this rank's K
+ * columns): the unrounded fp32 partial x W^T goes to word b*N+n of this rank's slot in every rank's exchange buffer
+ * instead; out and R are ignored (the consumer adds the residual). */
 int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, int N, int K,
-                int dtype, void* stream);
+                const pg_tp_exchange* ex, int dtype, void* stream);
 
 /* post-attention RMSNorm + gate/up projections + GeGLU (modeling_gemma.py:332,134).
  * w_gu = [Wgate; Wup] : [2F, D];  out: [B,F]. */
 int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w_gu, int B,
-                     int D, int F, float eps, int dtype, void* stream);
+                     int D, int F, float eps, const pg_tp_exchange* ex, void* x_out, int dtype, void* stream);
 
 /* final RMSNorm + tied lm_head + fp32 logits + greedy argmax (modeling_gemma.py:379,417-418;
  * inference.py:68).  logits: fp32 [B,V] (values rounded to the model dtype first, as the
@@ -164,7 +187,7 @@ int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w
  * on entry; decoded by pg_step_advance.  Ties go to the lowest index. */
 int pg_decode_lmhead(float* logits, const void* x, const void* norm_w, const void* w_emb,
                      int B, int D, int64_t V, float eps, unsigned long long* argmax_keys,
-                     int dtype, void* stream);
+                     const pg_tp_exchange* ex, void* x_out, int dtype, void* stream);
 
 /* End of a decode step, all on device (replaces the host side of inference.py:68-78):
  * token[b] = argmax(keys[b]) (or sampled[b] if sampled != NULL); next_ids[b] = token;
@@ -172,7 +195,9 @@ int pg_decode_lmhead(float* logits, const void* x, const void* norm_w, const voi
  * keys[b] = 0; *step_counter += 1 (by thread 0). */
 int pg_step_advance(int64_t* next_ids, int64_t* history, int hist_stride, int* step_counter,
                     unsigned long long* keys, const int64_t* sampled, int32_t* kv_len,
-                    int32_t* positions, int B, void* stream);
+                    int32_t* positions, int B, const pg_tp_exchange* keys_ex, void* stream);
+/* keys_ex != NULL (tensor parallel, greedy): token[b] is decoded from the largest key over the ranks' vocabulary
+ * shards, waited for in the key exchange filled by pg_tp_keys_push (ties: lowest global index). */
 
 /* Head of a cached decode step driven through the reference API (inference.py:56-63,
  * modeling_gemma.py:557-559): ids_dst[b] = ids_src[b]; positions[b] = position; and the reference's
@@ -183,7 +208,8 @@ int pg_decode_inputs(int64_t* ids_dst, const int64_t* ids_src, int32_t* position
                      const void* mask, int mask_kind, long long mask_n, int* bad_flag, int B, void* stream);
 
 /* torch.argmax(logits, -1) over fp32 [B,V] (inference.py:68).  keys_ws: device u64[B] holding 0
- * on entry (left 0 on exit). */
+ * on entry (left 0 on exit).  out == NULL: stop after the packed (value, index) keys, which stay in keys_ws
+ * (tensor parallel: the shard's keys go to pg_tp_keys_push). */
 int pg_argmax(int64_t* out, const float* logits, unsigned long long* keys_ws, int B, int64_t V,
               void* stream);
 
@@ -195,13 +221,20 @@ int pg_top_p_sample(int64_t* out, const float* logits, float* probs_ws, int B, i
                     float temperature, float top_p, unsigned long long seed,
                     const int* rng_offset, int* nucleus_size, void* stream);
 
-/* Tensor-parallel decoder: one-shot all-reduce(sum) of a small vector over NVLink peer memory (replaces the
- * NCCL all-reduce after o_proj / down_proj when the message is a few KB).  peers_dev: device array of `tp`
- * pointers to the ranks' symmetric buffers (each 2*cap_bytes of data slots + 2*16 uint32 flags, zeroed once);
- * step_counter: device int, the same on every rank, advanced by the kernel.  x is reduced in place; every
- * rank sums in rank order (bit-identical results).  *err_flag = 2 if a peer never arrived. */
-int pg_allreduce_oneshot(void* x, const void* peers_dev, int rank, int tp, int n, long long cap_bytes,
-                         int* step_counter, int* err_flag, int dtype, void* stream);
+/* ---- tensor-parallel decoder plumbing (pg_tp_exchange above) --------------------------------------------------
+ * pg_tp_begin_step: *epoch += 1, once at the head of every decode step (before its first producer).
+ * pg_tp_push: producer for a partial that a GEMM left in local memory (batched decode step): partial[n] fp32 ->
+ *   words 0..n-1 of this rank's slot in every rank's buffer.
+ * pg_rmsnorm_reduce: consumer for that step, one CTA per row: x_new = rnd(x_in + rnd(sum of partials)) -> x_out,
+ *   out = GemmaRMSNorm(x_new) (modeling_gemma.py:114-120).  x_out must not alias x_in.
+ * pg_tp_keys_push: vocabulary-split lm_head: keys[b] (value, LOCAL index) -> (value, index + rank * v_local) in
+ *   every rank's key slot; pg_step_advance(keys_ex) picks the winner. */
+int pg_tp_begin_step(int* epoch, void* stream);
+int pg_tp_push(const float* partial, long long n, const pg_tp_exchange* ex, void* stream);
+int pg_rmsnorm_reduce(void* out, void* x_out, const void* x_in, const void* w, int rows, int D, float eps,
+                      const pg_tp_exchange* ex, int dtype, void* stream);
+int pg_tp_keys_push(const unsigned long long* keys, int B, long long v_local, const pg_tp_exchange* ex,
+                    void* stream);
 
 /* KVCache.key_cache[layer] / value_cache[layer] view: gather pages into a contiguous
  * [B, nkv, T, hd] tensor (modeling_gemma.py:12-36 attribute parity). */

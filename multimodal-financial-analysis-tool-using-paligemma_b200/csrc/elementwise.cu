@@ -6,6 +6,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "tp_exchange.cuh"
 
 namespace pg {
 
@@ -304,14 +305,17 @@ __global__ void rope_append_kernel(T* __restrict__ q_out, const T* __restrict__ 
 // ------------------------------------------------------------------ decode-step bookkeeping
 __global__ void step_advance_kernel(int64_t* next_ids, int64_t* history, int hist_stride, int* step_counter,
                                     unsigned long long* keys, const int64_t* sampled, int32_t* kv_len,
-                                    int32_t* positions, int B) {
+                                    int32_t* positions, int B, TpEx ex) {
   const int b = threadIdx.x;
   const int step = step_counter ? *step_counter : 0;
   __syncthreads();
   if (b < B) {
-    int64_t tok = sampled ? sampled[b] : (int64_t)argmax_key_index(keys[b]);
+    // tensor parallel + greedy: the winning (value, global index) key over the ranks' vocabulary shards
+    int64_t tok = sampled ? sampled[b]
+                          : (int64_t)argmax_key_index(ex.peers ? tp_wait_best_key(ex, b) : keys[b]);
     next_ids[b] = tok;
-    if (history) history[(size_t)b * hist_stride + step] = tok;
+    // ring index: the step counter (also the sampler's RNG offset) keeps counting for the life of the engine
+    if (history && hist_stride > 0) history[(size_t)b * hist_stride + (unsigned)step % (unsigned)hist_stride] = tok;
     if (kv_len) kv_len[b] += 1;
     if (positions) positions[b] += 1;
     keys[b] = 0ull;
@@ -483,10 +487,13 @@ int pg_rope_append(void* q_out, const void* qkv, const float* inv_freq, const in
 
 int pg_step_advance(int64_t* next_ids, int64_t* history, int hist_stride, int* step_counter,
                     unsigned long long* keys, const int64_t* sampled, int32_t* kv_len, int32_t* positions,
-                    int B, void* stream) {
+                    int B, const pg_tp_exchange* keys_ex, void* stream) {
   PG_REQUIRE(B > 0 && B <= 1024, "step_advance: B=%d", B);
+  const TpEx tex = tp_ex_from(keys_ex);
+  PG_REQUIRE(!keys_ex || (tex.tp >= 2 && tex.tp <= TP_MAX_RANKS && (long long)B * 16 <= tex.slot_bytes),
+             "step_advance: bad tensor-parallel key exchange");
   step_advance_kernel<<<1, ((B + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(
-      next_ids, history, hist_stride, step_counter, keys, sampled, kv_len, positions, B);
+      next_ids, history, hist_stride, step_counter, keys, sampled, kv_len, positions, B, tex);
   return check_launch("step_advance");
 }
 
@@ -504,7 +511,7 @@ int pg_argmax(int64_t* out, const float* logits, unsigned long long* keys, int B
   int gx = (int)((V + 256 * 8 - 1) / (256 * 8));
   if (gx > 148) gx = 148;
   argmax_partial_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(keys, logits, V);
-  argmax_final_kernel<<<1, ((B + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(out, keys, B);
+  if (out) argmax_final_kernel<<<1, ((B + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(out, keys, B);
   return check_launch("argmax");
 }
 

@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tp_exchange.cuh"
 
 namespace pg {
 
@@ -170,15 +171,78 @@ __device__ __forceinline__ void norm_rows_to_smem(float* xs, const T* __restrict
   __syncthreads();
 }
 
+// Tensor-parallel variant of the prologue (tp_exchange.cuh): the input row is not in memory yet -- its last term
+// is still spread over the ranks as fp32 partials of the previous o_proj / down_proj.  Every CTA waits for the
+// partials in its local exchange buffer, sums them in rank order, rounds once (the reference's projection output),
+// adds the residual stream x_in (rounded again: `residual + hidden_states`), keeps the new stream in shared memory
+// and normalises it there.  CTA 0 also writes the new stream to x_out for the next residual add.
+template <typename T, int NB>
+__device__ __forceinline__ void reduce_norm_rows_to_smem(float* xs, const T* __restrict__ x_in, T* __restrict__ x_out,
+                                                         const T* __restrict__ w, int D, float eps, const TpEx& ex) {
+  __shared__ float red_tp[NB][GEMV_WARPS];
+  const uint32_t seq = tp_seq(ex);
+  bool dead = tp_failed(ex);
+  float ss[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+  const int half = D / 2;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    for (int c2 = threadIdx.x; c2 < half; c2 += GEMV_THREADS) {
+      const size_t i = (size_t)b * D + 2 * c2;
+      const float2 p = tp_reduce_pair(ex, seq, (long long)(i >> 1), dead);
+      const float v0 = rnd<T>(to_f<T>(x_in[i]) + rnd<T>(p.x));
+      const float v1 = rnd<T>(to_f<T>(x_in[i + 1]) + rnd<T>(p.y));
+      xs[i] = v0;
+      xs[i + 1] = v1;
+      ss[b] += v0 * v0 + v1 * v1;
+      if (blockIdx.x == 0 && x_out) {
+        x_out[i] = from_f<T>(v0);
+        x_out[i + 1] = from_f<T>(v1);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float v = warp_sum(ss[b]);
+    if (lane == 0) red_tp[b][wid] = v;
+  }
+  __syncthreads();
+  float inv[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < GEMV_WARPS; ++i) t += red_tp[b][i];
+    inv[b] = rsqrtf(t / (float)D + eps);
+  }
+  for (int c = threadIdx.x; c < D; c += GEMV_THREADS) {
+    const float g = 1.0f + to_f<T>(w[c]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) xs[(size_t)b * D + c] = rnd<T>((xs[(size_t)b * D + c] * inv[b]) * g);
+  }
+  __syncthreads();
+}
+
+// TPX is a template parameter so the single-GPU instantiations keep their register budget (72 registers for the
+// gate/up kernel = 3 CTAs per SM; the exchange code would push it past 100)
+template <typename T, int NB, bool TPX>
+__device__ __forceinline__ void prologue_rows(float* xs, const T* __restrict__ x, T* __restrict__ x_out,
+                                              const T* __restrict__ w, int D, float eps, const TpEx& ex) {
+  if constexpr (TPX) reduce_norm_rows_to_smem<T, NB>(xs, x, x_out, w, D, eps, ex);
+  else norm_rows_to_smem<T, NB>(xs, x, w, D, eps);
+}
+
 // ------------------------------------------------------------------ RMSNorm + QKV + RoPE + KV append
-template <typename T, int NB, int QKV_U>
+template <typename T, int NB, int QKV_U, bool TPX>
 __global__ void __launch_bounds__(GEMV_THREADS)
 decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __restrict__ norm_w,
                   const T* __restrict__ W, const float* __restrict__ inv_freq,
                   const int32_t* __restrict__ positions, T* __restrict__ k_pool, T* __restrict__ v_pool,
                   const int32_t* __restrict__ page_table, int pt_stride, int page_size,
                   const int32_t* __restrict__ kv_len, int D, int nq, int nkv, int hd, float eps, int max_pos,
-                  Prefetch pf) {
+                  Prefetch pf, TpEx ex, T* __restrict__ x_out) {
   extern __shared__ __align__(16) float xs[];
   pdl_launch_dependents();
   l2_prefetch_slice(pf);
@@ -193,7 +257,7 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
   RowStreamer<T, NB, 2, QKV_U, true> rs;
   rs.prime(warp, units, 0, D, rows);
   pdl_wait();
-  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
+  prologue_rows<T, NB, TPX>(xs, x, x_out, norm_w, D, eps, ex);
   rs.run(units, nwarps, xs, nullptr, D, 0, D, rows, [&](long long u, float (&acc)[2][NB]) {
     if (lane < NB) {
       const int h = (int)u / half, j = (int)u % half;
@@ -232,10 +296,10 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
 
 // ------------------------------------------------------------------ GEMV + residual (o_proj / down_proj)
 // KS warps share one output row (split along K, combined through shared memory).
-template <typename T, int NB, int KS>
+template <typename T, int NB, int KS, bool TPX>
 __global__ void __launch_bounds__(GEMV_THREADS)
 gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ W, const T* __restrict__ R,
-                int N, int K, Prefetch pf) {
+                int N, int K, Prefetch pf, TpEx ex) {
   constexpr int V = Vec<T>::N;
   constexpr int ROWS_PER_CTA = GEMV_WARPS / KS;
   __shared__ float part[2][GEMV_WARPS][NB];
@@ -254,6 +318,10 @@ gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restric
   RowStreamer<T, NB, 1, 8, false> rs;
   rs.prime(blockIdx.x, n_iter, k_begin, k_end, rows);
   pdl_wait();
+  // tensor parallel: this rank's fp32 partial goes to every rank's exchange buffer (this rank's own included)
+  // instead of `out`; the next kernel's prologue sums the partials and adds the residual
+  uint32_t seq = 0u;
+  if constexpr (TPX) seq = tp_seq(ex);
   int parity = 0;
   rs.run(n_iter, gridDim.x, nullptr, x, K, k_begin, k_end, rows, [&](long long it, float (&acc)[1][NB]) {
     const long long n = it * ROWS_PER_CTA + rsub;
@@ -278,18 +346,22 @@ gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restric
       float a = 0.f;
 #pragma unroll
       for (int b = 0; b < NB; ++b) if (b == lane) a = acc[0][b];
-      float v = rnd<T>(a);
-      if (R) v = rnd<T>(to_f<T>(R[(size_t)lane * N + n]) + v);
-      out[(size_t)lane * N + n] = from_f<T>(v);
+      if constexpr (TPX) {
+        for (int p = 0; p < ex.tp; ++p) tp_store_word(tp_slot(ex, p, seq, ex.rank), (long long)lane * N + n, a, seq);
+      } else {
+        float v = rnd<T>(a);
+        if (R) v = rnd<T>(to_f<T>(R[(size_t)lane * N + n]) + v);
+        out[(size_t)lane * N + n] = from_f<T>(v);
+      }
     }
   });
 }
 
 // ------------------------------------------------------------------ RMSNorm + gate/up + GeGLU
-template <typename T, int NB>
+template <typename T, int NB, bool TPX>
 __global__ void __launch_bounds__(GEMV_THREADS)
 decode_gateup_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ norm_w,
-                     const T* __restrict__ W, int D, int F, float eps, Prefetch pf) {
+                     const T* __restrict__ W, int D, int F, float eps, Prefetch pf, TpEx ex, T* __restrict__ x_out) {
   extern __shared__ __align__(16) float xs[];
   pdl_launch_dependents();
   l2_prefetch_slice(pf);
@@ -302,7 +374,7 @@ decode_gateup_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __re
   RowStreamer<T, NB, 2, 4, true> rs;
   rs.prime(warp, F, 0, D, rows);
   pdl_wait();
-  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
+  prologue_rows<T, NB, TPX>(xs, x, x_out, norm_w, D, eps, ex);
   rs.run(F, nwarps, xs, nullptr, D, 0, D, rows, [&](long long f, float (&acc)[2][NB]) {
     if (lane < NB) {
       float g = 0.f, u = 0.f;
@@ -315,11 +387,11 @@ decode_gateup_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __re
 }
 
 // ------------------------------------------------------------------ final RMSNorm + lm_head + argmax
-template <typename T, int NB>
+template <typename T, int NB, bool TPX>
 __global__ void __launch_bounds__(GEMV_THREADS)
 decode_lmhead_kernel(float* __restrict__ logits, const T* __restrict__ x, const T* __restrict__ norm_w,
                      const T* __restrict__ W, int D, long long V, float eps, unsigned long long* keys,
-                     Prefetch pf) {
+                     Prefetch pf, TpEx ex, T* __restrict__ x_out) {
   extern __shared__ __align__(16) float xs[];
   __shared__ unsigned long long best_s[GEMV_WARPS][NB];
   pdl_launch_dependents();
@@ -334,7 +406,7 @@ decode_lmhead_kernel(float* __restrict__ logits, const T* __restrict__ x, const 
   RowStreamer<T, NB, 2, 4, true> rs;
   rs.prime(warp, units, 0, D, rows);
   pdl_wait();
-  norm_rows_to_smem<T, NB>(xs, x, norm_w, D, eps);
+  prologue_rows<T, NB, TPX>(xs, x, x_out, norm_w, D, eps, ex);
   unsigned long long best = 0ull;  // lane b < NB tracks batch row b
   rs.run(units, nwarps, xs, nullptr, D, 0, D, rows, [&](long long u, float (&acc)[2][NB]) {
     if (lane < NB) {
@@ -384,10 +456,11 @@ static int dispatch_nb(int B, F&& f) {
 
 // Persistent-style grids: a multiple of the 148 SMs.  Defaults measured on B200 (tools/kernel_sweep.py):
 // 3 CTAs/SM for the RMSNorm-prologue kernels (72-register, 8 KB smem), 4 for the plain GEMV.
-static int grid_for_units(long long units, int per_cta, bool norm_kernel) {
+static int grid_for_units(long long units, int per_cta, bool norm_kernel, bool tp = false) {
   long long g = (units + per_cta - 1) / per_cta;
   static const int cps_norm = env_int("PG_CPS_NORM", 3), cps_res = env_int("PG_CPS_RES", 6);
-  const long long cap = 148LL * (norm_kernel ? cps_norm : cps_res);
+  static const int cps_tp = env_int("PG_CPS_TP", 2);   // the exchange prologue costs ~110 registers: 2 CTAs per SM
+  const long long cap = 148LL * (norm_kernel ? (tp ? cps_tp : cps_norm) : cps_res);
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -396,17 +469,30 @@ static int grid_for_units(long long units, int per_cta, bool norm_kernel) {
 using namespace pg;
 
 #define PG_GR(KS_)                                                                                        \
-  return launch_pdl("gemv_res", gemv_res_kernel<T, NB, KS_>,                                              \
+  if (ex)                                                                                                 \
+    return launch_pdl("gemv_res", gemv_res_kernel<T, NB, KS_, true>,                                      \
+                      dim3(grid_for_units(cdiv(N, GEMV_WARPS / KS_), 1, false)), dim3(GEMV_THREADS), 0, st,   \
+                      (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf, tex);                     \
+  return launch_pdl("gemv_res", gemv_res_kernel<T, NB, KS_, false>,                                       \
                     dim3(grid_for_units(cdiv(N, GEMV_WARPS / KS_), 1, false)), dim3(GEMV_THREADS), 0, st,     \
-                    (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf)
+                    (T*)out, (const T*)x, (const T*)W, (const T*)R, N, K, pf, tex)
+
+#define PG_QKV(U_, TPX_)                                                                                          \
+  return launch_pdl("decode_qkv", decode_qkv_kernel<T, NB, U_, TPX_>, dim3(grid_for_units(units, GEMV_WARPS, true, TPX_)), \
+                    dim3(GEMV_THREADS), smem, (cudaStream_t)stream, (T*)q_out, (const T*)x, (const T*)norm_w,         \
+                    (const T*)w_qkv, inv_freq, positions, (T*)k_pool, (T*)v_pool, page_table, pt_stride, page_size,  \
+                    kv_len, D, nq, nkv, hd, eps, max_pos, pf, tex, (T*)x_out)
 
 extern "C" {
 
 int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_qkv, const float* inv_freq,
                   const int32_t* positions, void* k_pool, void* v_pool, const int32_t* page_table,
                   int pt_stride, int page_size, const int32_t* kv_len, int B, int D, int nq, int nkv, int hd,
-                  float eps, int max_pos, int dtype, void* stream) {
+                  float eps, int max_pos, const pg_tp_exchange* ex, void* x_out, int dtype, void* stream) {
   const Prefetch pf = take_prefetch();
+  const TpEx tex = tp_ex_from(ex);
+  PG_REQUIRE(!ex || (tex.tp >= 2 && tex.tp <= TP_MAX_RANKS && D % 2 == 0 && (long long)B * D * 8 <= tex.slot_bytes),
+             "decode_qkv: bad tensor-parallel exchange");
   PG_REQUIRE(hd % 2 == 0, "decode_qkv: odd head_dim");
   const int units = (nq + 2 * nkv) * (hd / 2);
   PG_DISPATCH_DTYPE(dtype, T, {
@@ -416,23 +502,20 @@ int pg_decode_qkv(void* q_out, const void* x, const void* norm_w, const void* w_
       size_t smem = (size_t)NB * D * sizeof(float);
       PG_REQUIRE(smem <= 200 * 1024, "decode_qkv: B*D too large for shared memory");
       static const int u8 = env_int("PG_QKV_U8", 1);
-      if (NB <= 2 && u8)
-        return launch_pdl("decode_qkv", decode_qkv_kernel<T, NB, 8>, dim3(grid_for_units(units, GEMV_WARPS, true)),
-                          dim3(GEMV_THREADS), smem, (cudaStream_t)stream, (T*)q_out, (const T*)x, (const T*)norm_w,
-                          (const T*)w_qkv, inv_freq, positions, (T*)k_pool, (T*)v_pool, page_table, pt_stride,
-                          page_size, kv_len, D, nq, nkv, hd, eps, max_pos, pf);
-      return launch_pdl("decode_qkv", decode_qkv_kernel<T, NB, 4>, dim3(grid_for_units(units, GEMV_WARPS, true)),
-                        dim3(GEMV_THREADS), smem, (cudaStream_t)stream, (T*)q_out, (const T*)x, (const T*)norm_w,
-                        (const T*)w_qkv, inv_freq, positions, (T*)k_pool, (T*)v_pool, page_table, pt_stride,
-                        page_size, kv_len, D, nq, nkv, hd, eps, max_pos, pf);
+      if (ex) { PG_QKV(4, true); }
+      if (NB <= 2 && u8) { PG_QKV(8, false); }
+      PG_QKV(4, false);
     });
   });
   return PG_OK;
 }
 
-int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, int N, int K, int dtype,
-                void* stream) {
+int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, int N, int K,
+                const pg_tp_exchange* ex, int dtype, void* stream) {
   const Prefetch pf = take_prefetch();
+  const TpEx tex = tp_ex_from(ex);
+  PG_REQUIRE(!ex || (tex.tp >= 2 && tex.tp <= TP_MAX_RANKS && (long long)B * N * 8 <= tex.slot_bytes),
+             "gemv_res: bad tensor-parallel exchange");
   PG_DISPATCH_DTYPE(dtype, T, {
     PG_REQUIRE(K % Vec<T>::N == 0, "gemv_res: K=%d not vector aligned", K);
     return dispatch_nb(B, [&](auto nb) {
@@ -449,35 +532,51 @@ int pg_gemv_res(void* out, const void* x, const void* W, const void* R, int B, i
 }
 
 int pg_decode_gateup(void* out, const void* x, const void* norm_w, const void* w_gu, int B, int D, int F,
-                     float eps, int dtype, void* stream) {
+                     float eps, const pg_tp_exchange* ex, void* x_out, int dtype, void* stream) {
   const Prefetch pf = take_prefetch();
+  const TpEx tex = tp_ex_from(ex);
+  PG_REQUIRE(!ex || (tex.tp >= 2 && tex.tp <= TP_MAX_RANKS && D % 2 == 0 && (long long)B * D * 8 <= tex.slot_bytes),
+             "decode_gateup: bad tensor-parallel exchange");
   PG_DISPATCH_DTYPE(dtype, T, {
     PG_REQUIRE(D % Vec<T>::N == 0, "decode_gateup: D=%d not vector aligned", D);
     return dispatch_nb(B, [&](auto nb) {
       constexpr int NB = decltype(nb)::value;
       size_t smem = (size_t)NB * D * sizeof(float);
       PG_REQUIRE(smem <= 200 * 1024, "decode_gateup: B*D too large for shared memory");
-      return launch_pdl("decode_gateup", decode_gateup_kernel<T, NB>, dim3(grid_for_units(F, GEMV_WARPS, true)),
+      if (ex)
+        return launch_pdl("decode_gateup", decode_gateup_kernel<T, NB, true>, dim3(grid_for_units(F, GEMV_WARPS, true, true)),
+                          dim3(GEMV_THREADS), smem, (cudaStream_t)stream, (T*)out, (const T*)x, (const T*)norm_w,
+                          (const T*)w_gu, D, F, eps, pf, tex, (T*)x_out);
+      return launch_pdl("decode_gateup", decode_gateup_kernel<T, NB, false>, dim3(grid_for_units(F, GEMV_WARPS, true)),
                         dim3(GEMV_THREADS), smem, (cudaStream_t)stream, (T*)out, (const T*)x, (const T*)norm_w,
-                        (const T*)w_gu, D, F, eps, pf);
+                        (const T*)w_gu, D, F, eps, pf, tex, (T*)x_out);
     });
   });
   return PG_OK;
 }
 
 int pg_decode_lmhead(float* logits, const void* x, const void* norm_w, const void* w_emb, int B, int D,
-                     int64_t V, float eps, unsigned long long* argmax_keys, int dtype, void* stream) {
+                     int64_t V, float eps, unsigned long long* argmax_keys, const pg_tp_exchange* ex, void* x_out,
+                     int dtype, void* stream) {
   const Prefetch pf = take_prefetch();
+  const TpEx tex = tp_ex_from(ex);
+  PG_REQUIRE(!ex || (tex.tp >= 2 && tex.tp <= TP_MAX_RANKS && D % 2 == 0 && (long long)B * D * 8 <= tex.slot_bytes),
+             "decode_lmhead: bad tensor-parallel exchange");
   PG_DISPATCH_DTYPE(dtype, T, {
     PG_REQUIRE(D % Vec<T>::N == 0, "decode_lmhead: D=%d not vector aligned", D);
     return dispatch_nb(B, [&](auto nb) {
       constexpr int NB = decltype(nb)::value;
       size_t smem = (size_t)NB * D * sizeof(float);
       PG_REQUIRE(smem <= 200 * 1024, "decode_lmhead: B*D too large for shared memory");
-      return launch_pdl("decode_lmhead", decode_lmhead_kernel<T, NB>,
+      if (ex)
+        return launch_pdl("decode_lmhead", decode_lmhead_kernel<T, NB, true>,
+                          dim3(grid_for_units((V + 1) / 2, GEMV_WARPS, true, true)), dim3(GEMV_THREADS), smem,
+                          (cudaStream_t)stream, logits, (const T*)x, (const T*)norm_w, (const T*)w_emb, D,
+                          (long long)V, eps, argmax_keys, pf, tex, (T*)x_out);
+      return launch_pdl("decode_lmhead", decode_lmhead_kernel<T, NB, false>,
                         dim3(grid_for_units((V + 1) / 2, GEMV_WARPS, true)), dim3(GEMV_THREADS), smem,
                         (cudaStream_t)stream, logits, (const T*)x, (const T*)norm_w, (const T*)w_emb, D,
-                        (long long)V, eps, argmax_keys, pf);
+                        (long long)V, eps, argmax_keys, pf, tex, (T*)x_out);
     });
   });
   return PG_OK;

@@ -381,6 +381,8 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         if attention_mask is None:
             raise ValueError("attention_mask must be provided")
         self._raise_deferred_mask_error()
+        if self._engine is not None:
+            self._engine.check_errors()      # bad ids met by an earlier cached step (pinned flag, no sync)
         # cached single-token steps check the mask on the device (pg_decode_inputs) and report it at the next call
         # instead of paying the reference's host synchronisation (modeling_gemma.py:559) on every token
         fast = (kv_cache is not None and input_ids is not None and inputs_embeds is None and labels is None
@@ -406,6 +408,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
             if pixel_values is not None:
                 feats = eng.encode_images(pixel_values.to(eng.device))
             logits = eng.text_forward(input_ids, feats, paged, position_value=int(attention_mask.shape[1]))
+            eng.check_errors(sync=True)      # this path already synchronised for the mask check above
         if return_dict:
             out = {"logits": logits}
             if kv_cache is not None:
@@ -431,7 +434,9 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         else:
             ds.ids.copy_(input_ids.reshape(-1), non_blocking=True)
             ds.pos.fill_(position)
+        ds.want_full_logits = True       # tensor parallel: forward() returns the whole vocabulary row
         ds.run_steps(paged, 1)
+        # a fresh tensor per call, as the reference returns (callers keep earlier steps' logits)
         return ds.logits.clone().view(paged.batch, 1, -1)
 
     def _raise_deferred_mask_error(self):

@@ -45,18 +45,21 @@ SIGNATURES = {
                         _i, _i, _i, _i, _f, _i, _i, _vp],
     "pg_set_next_prefetch": [_vp, _ll],
     "pg_decode_qkv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f,
-                      _i, _i, _vp],
+                      _i, _vp, _vp, _i, _vp],
     "pg_decode_attention_ws_floats": [_i, _i, _i, _i],
     "pg_decode_attention": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _i,
                             _i, _vp],
-    "pg_gemv_res": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "pg_decode_gateup": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
-    "pg_decode_lmhead": [_vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _i, _vp],
-    "pg_step_advance": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "pg_gemv_res": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    "pg_decode_gateup": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
+    "pg_decode_lmhead": [_vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _vp, _vp, _i, _vp],
+    "pg_step_advance": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "pg_decode_inputs": [_vp, _vp, _vp, _i, _vp, _i, _ll, _vp, _i, _vp],
     "pg_argmax": [_vp, _vp, _vp, _i, _ll, _vp],
     "pg_top_p_sample": [_vp, _vp, _vp, _i, _ll, _f, _f, _ull, _vp, _vp, _vp],
-    "pg_allreduce_oneshot": [_vp, _vp, _i, _i, _i, _ll, _vp, _vp, _i, _vp],
+    "pg_tp_begin_step": [_vp, _vp],
+    "pg_tp_push": [_vp, _ll, _vp, _vp],
+    "pg_rmsnorm_reduce": [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _i, _vp],
+    "pg_tp_keys_push": [_vp, _i, _ll, _vp, _vp],
     "pg_kv_gather": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPE = {"pg_last_error": C.c_char_p, "pg_launch_count": _ull, "pg_decode_attention_ws_floats": _ll}
@@ -93,6 +96,11 @@ def check(rc: int, what: str = "") -> None:
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def exref(ex):
+    """`const pg_tp_exchange*` argument: address of a pg_b200.dist.Exchange (None -> NULL = not tensor parallel)."""
+    return None if ex is None else C.addressof(ex)
 
 
 def stream() -> int:

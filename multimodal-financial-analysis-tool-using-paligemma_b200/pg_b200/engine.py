@@ -22,8 +22,8 @@ from typing import Dict, List, Mapping, Optional
 import torch
 
 from . import _cabi as cabi
-from ._cabi import ptr
-from .dist import TP, check_divisible, combine_argmax_keys, shard_rows, shard_text_layer
+from ._cabi import exref, ptr
+from .dist import TP, check_divisible, combine_argmax_keys, shard_batch, shard_rows, shard_text_layer
 
 
 def _get(obj, name, default=None):
@@ -162,9 +162,25 @@ class PaliGemmaEngine:
         self.k_pool = torch.zeros((d.L, self.num_pages, page_size, d.nkv * d.hd), dtype=self.dtype, device=self.device)
         self.v_pool = torch.zeros_like(self.k_pool)
         self._free = list(range(self.num_pages - 1, -1, -1))
-        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # pinned, device-mapped: kernels store to it only when they meet a bad id, the host reads it without a sync
+        self.err_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._err_np = self.err_flag.numpy()
         self.max_splits = 32
         self._decode_states: Dict[tuple, "DecodeState"] = {}
+        # tensor parallel: the peer-memory exchange the decode kernels use instead of collectives (dist.Fabric)
+        self.fabric = self.tp.ensure_fabric(d.D, self.device) if self.tp.active else None
+        if self.fabric is not None and 2 * d.L + 2 > 4096:
+            raise ValueError("too many layers for the exchange sequence numbering")
+
+    def kv_pool_bytes(self) -> int:
+        return 2 * self.k_pool.numel() * self.k_pool.element_size()
+
+    def kv_bytes_in_use(self) -> int:
+        """Bytes of the pre-allocated pool that hold pages of live sequences (the reference's KVCache grows by
+        torch.cat, so its allocator peak tracks this number; ours pre-allocates the pool)."""
+        d = self.dims
+        used = self.num_pages - len(self._free)
+        return 2 * d.L * used * self.page_size * d.nkv * d.hd * self.k_pool.element_size()
 
     # ------------------------------------------------------------------ weights
     def _w(self, weights, key):
@@ -411,6 +427,12 @@ class PaliGemmaEngine:
         tokens get positions 0..q-1; with a non-empty cache every new token gets
         `position_value` (the attention-mask length).  Returns fp32 logits (B,q,V) or, with
         logits='last', (B,1,V)."""
+        return self.tp.run(self.text_forward_gen(input_ids, image_features, kv, position_value, logits))
+
+    def text_forward_gen(self, input_ids, image_features, kv, position_value=None, logits="all"):
+        """text_forward as a launch generator: yields ("all_reduce", t) / ("all_gather", out, t) where the tensor-parallel
+        ranks must meet (TP.run performs them with torch.distributed, LockstepGroup for emulated ranks) and returns
+        the logits.  The prefill keeps collectives: its messages are (B*q, D) rows, bandwidth- not latency-sized."""
         d, L, st = self.dims, cabi.lib(), cabi.stream()
         B, q = input_ids.shape
         T = B * q
@@ -430,7 +452,6 @@ class PaliGemmaEngine:
             img = None if image_features is None or image_features.numel() == 0 else \
                 image_features.reshape(-1, d.D).to(self.dtype).contiguous()
             x = self._new(T, d.D)
-            self.err_flag.zero_()
             cabi.check(L.pg_embed_merge(ptr(x), ptr(ids), ptr(self.emb), ptr(img), T, d.D, d.V,
                                         d.image_token_index, d.pad_token_id, 0 if img is None else img.shape[0],
                                         self.img_div, self.normalizer, ptr(self.err_flag), self.dt, st), "embed_merge")
@@ -458,11 +479,13 @@ class PaliGemmaEngine:
                                               ptr(kv.kv_len), 0, q, B, q, nq, d.nkv, d.hd, scale_div, 1, self.dt, st),
                                "attention")
                 self._gemm(x2, att, w["o"], None, x if tp.rank == 0 else None, res_epi)
-                tp.all_reduce(x2)
+                if tp.active:
+                    yield ("all_reduce", x2)
                 cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), T, d.D, d.eps, self.dt, st), "rmsnorm")
                 self._gemm(g, n, w["gu"], None, None, cabi.EPI_GEGLU)
                 self._gemm(x, g, w["down"], None, x2 if tp.rank == 0 else None, res_epi)
-                tp.all_reduce(x)
+                if tp.active:
+                    yield ("all_reduce", x)
             kv.kv_len.add_(q)
             kv.length = cached + q
             if logits == "last":
@@ -471,25 +494,56 @@ class PaliGemmaEngine:
             out = self._new(rows, self.V_l, dtype=torch.float32)
             if rows < self.batched_min:
                 # a handful of rows: the weight-streaming lm_head kernel (final norm fused) beats a GEMM tile
-                cabi.check(L.pg_decode_lmhead(ptr(out), ptr(x), ptr(self.final_norm), ptr(self.lm_head), rows, d.D,
-                                              self.V_l, d.eps, None, self.dt, st), "lm_head")
+                for r0 in range(0, rows, cabi.MAX_DECODE_BATCH):
+                    nr = min(cabi.MAX_DECODE_BATCH, rows - r0)
+                    cabi.check(L.pg_decode_lmhead(ptr(out[r0:]), ptr(x[r0:]), ptr(self.final_norm), ptr(self.lm_head), nr, d.D,
+                                                  self.V_l, d.eps, None, None, None, self.dt, st), "lm_head")
             else:
                 h = self._new(rows, d.D)
                 cabi.check(L.pg_rmsnorm(ptr(h), ptr(x), ptr(self.final_norm), rows, d.D, d.eps, self.dt, st), "final norm")
                 self._gemm(out, h, self.lm_head, out_f32=True)
             if tp.active:  # vocab shards -> full rows
-                gathered = tp.all_gather(self._new(tp.size, rows, self.V_l, dtype=torch.float32), out)
+                gathered = self._new(tp.size, rows, self.V_l, dtype=torch.float32)
+                yield ("all_gather", gathered, out)
                 out = gathered.permute(1, 0, 2).reshape(rows, d.V)
             return out.view(B, -1, d.V)
         finally:
             if temp:
                 kv.release()
 
-    def check_errors(self) -> None:
-        """Raise if a kernel flagged an id problem (image token without image rows, id out of range):
-        the reference raises from masked_scatter / embedding for the same inputs."""
-        if int(self.err_flag.item()) != 0:
-            self.err_flag.zero_()
+    def encode_images_dp(self, pixels: torch.Tensor) -> torch.Tensor:
+        """Batch-level data parallelism for the vision tower: every rank encodes its contiguous share
+        of the images (SigLIP + projector, modeling_gemma.py:568-571) and the (B, P, D) features are all-gathered
+        over NCCL, 1 MB per image in bf16.  Fewer images than ranks: every rank encodes them all (replicated)."""
+        tp = self.tp
+        B = pixels.shape[0]
+        if not tp.active or B < tp.size or tp.emulated:
+            return self.encode_images(pixels)
+        import torch.distributed as dist
+        d = self.dims
+        lo, hi = shard_batch(B, tp.rank, tp.size)
+        per = -(-B // tp.size)                                   # the largest share; smaller ones are padded
+        mine = self._new(per, d.P, d.D)
+        mine[:hi - lo].copy_(self.encode_images(pixels[lo:hi].contiguous()))
+        allf = self._new(tp.size, per, d.P, d.D)
+        dist.all_gather_into_tensor(allf.view(tp.size * per, d.P, d.D), mine, group=tp.group)
+        if B % tp.size == 0:
+            return allf.view(B, d.P, d.D)
+        return torch.cat([allf[r, :shard_batch(B, r, tp.size)[1] - shard_batch(B, r, tp.size)[0]] for r in range(tp.size)])
+
+    def check_errors(self, sync: bool = False) -> None:
+        """Raise if a kernel flagged an id problem (image token without image rows, id out of range): the reference
+        raises from masked_scatter / embedding for the same inputs.  The flag lives in pinned host memory, so the
+        check itself never synchronises; callers that are at a synchronisation point anyway (prefill forward, end of
+        generate(), the scheduler's per-chunk read-back) pass sync=True to see this call's own kernels, the per-token
+        decode path reports at the next call (like the deferred mask check)."""
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        if self._err_np[0] != 0 or (self.tp.fabric is not None and self.tp.fabric.lost_peer()):
+            lost = self.tp.fabric is not None and self.tp.fabric.lost_peer()
+            self._err_np[0] = 0
+            if lost:
+                raise RuntimeError("tensor-parallel exchange timed out waiting for a peer rank")
             raise RuntimeError("input_ids held an image token with no image feature left, or an id outside the vocabulary")
 
     # ------------------------------------------------------------------ decode (q_len == 1)
@@ -530,7 +584,7 @@ class DecodeState:
         self.local_logits = self.logits if not tp.active else torch.zeros((batch, eng.V_l), dtype=torch.float32, device=dev)
         self.gather_logits = torch.zeros((tp.size, batch, eng.V_l), dtype=torch.float32, device=dev) if tp.active else None
         self.gather_keys = torch.zeros((tp.size, batch), dtype=torch.int64, device=dev) if tp.active else None
-        self.want_full_logits = True   # TP: gather the vocab shards every step (API parity / sampling)
+        self.want_full_logits = False  # TP: also all-gather the vocabulary shards of the logits every step (forward() API)
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.pf_cap_mb = float(os.environ.get("PG_PF_MB", "0"))   # L2 prefetch distance per launch (0 = off)
         self.kv: Optional[PagedKV] = None
@@ -548,66 +602,139 @@ class DecodeState:
 
     # one decode step: kernels only, no host sync, capturable
     def launch_step(self, kv: PagedKV, sample: Optional[tuple] = None, advance: bool = True) -> None:
+        self.eng.tp.run(self.step_gen(kv, sample, advance))
+
+    def step_gen(self, kv: PagedKV, sample: Optional[tuple] = None, advance: bool = True):
+        """The step as a launch generator (one `yield` per kernel; see dist.TP.run / dist.LockstepGroup)."""
+        if self.B >= self.eng.batched_min:
+            yield from self._step_batched_gen(kv, sample, advance)
+        else:
+            yield from self._step_gemv_gen(kv, sample, advance)
+
+    def _fabric(self):
+        """The peer-memory exchange when this step can use it (rows fit one slot, one GEMV sub-batch)."""
+        fab = self.eng.fabric
+        if fab is None or self.B > fab.MAX_ROWS:
+            return None
+        if self.B < self.eng.batched_min and self.B > cabi.MAX_DECODE_BATCH:
+            return None
+        return fab
+
+    def layer_gemv_gen(self, li: int, kv: PagedKV, fab, first: bool):
+        """Decoder layer `li` of the GEMV step (batch <= 8).  Residual stream: enters in self.x (`first`) or, tensor
+        parallel with the exchange, as self.x2 + the pending down_proj partials; leaves in self.x (no exchange) or as
+        self.x2 + pending partials (exchange)."""
         eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
-        B, dt = self.B, self.eng.dt
+        B, dt, MB = self.B, self.eng.dt, cabi.MAX_DECODE_BATCH
+        tp, nq, F_l = eng.tp, eng.nq_l, eng.F_l
+        w = eng.t_layers[li]
+        kp, vp = eng.k_pool[li], eng.v_pool[li]
+        x, x2 = self.x, self.x2
+        stride = 2 * d.L + 2
+        scale_div = float(math.sqrt(d.hd))
         cap = self.pf_cap_mb
-        if B >= eng.batched_min and not eng.tp.active:
-            return self._launch_step_batched(kv, sample, advance)
+        nxt = eng.t_layers[li + 1]["qkv"] if li + 1 < len(eng.t_layers) else eng.lm_head
+        self._pf(w["o"])                                   # qkv pulls o_proj's weights
+        ex_in = fab.x(2 * li, stride) if (fab is not None and not first) else None
+        for b0 in range(0, B, MB):
+            nb = min(MB, B - b0)
+            xin = x2 if ex_in is not None else x
+            cabi.check(L.pg_decode_qkv(ptr(self.q[b0:]), ptr(xin[b0:]), ptr(w["ln1"]), ptr(w["qkv"]), ptr(eng.inv_freq),
+                                       ptr(self.pos[b0:]), ptr(kp), ptr(vp), ptr(kv.page_table[b0:]), kv.max_pages,
+                                       eng.page_size, ptr(kv.kv_len[b0:]), nb, d.D, nq, d.nkv, d.hd, d.eps,
+                                       d.max_pos, exref(ex_in), ptr(x[b0:]) if ex_in is not None else None, dt, st),
+                       "decode_qkv")
+            yield
+        self._pf(w["gu"])                                  # attention pulls the head of gate/up
+        cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
+                                         kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, nq, d.nkv, d.hd,
+                                         scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
+                   "decode_attention")
+        yield
+        if fab is not None:
+            # producer -> consumer pairs: the partial sums travel inside the kernels (csrc/tp_exchange.cuh)
+            ex_o, ex_d = fab.x(2 * li + 1, stride), fab.x(2 * li + 2, stride)
+            cabi.check(L.pg_gemv_res(None, ptr(self.att), ptr(w["o"]), None, B, d.D, nq * d.hd, exref(ex_o), dt, st), "o_proj")
+            yield
+            cabi.check(L.pg_decode_gateup(ptr(self.g), ptr(x), ptr(w["ln2"]), ptr(w["gu"]), B, d.D, F_l, d.eps,
+                                          exref(ex_o), ptr(x2), dt, st), "gateup")
+            yield
+            cabi.check(L.pg_gemv_res(None, ptr(self.g), ptr(w["down"]), None, B, d.D, F_l, exref(ex_d), dt, st), "down_proj")
+            yield
+            return
+        for b0 in range(0, B, MB):
+            nb = min(MB, B - b0)
+            if b0 == 0:
+                self._pf(w["gu"], start_mb=cap)            # o_proj pulls the next slice of gate/up
+            # tensor parallel over collectives: only rank 0 adds the residual, so it enters the all-reduced sum once
+            cabi.check(L.pg_gemv_res(ptr(x2[b0:]), ptr(self.att[b0:]), ptr(w["o"]),
+                                     ptr(x[b0:]) if tp.rank == 0 else None, nb, d.D, nq * d.hd, None, dt, st), "o_proj")
+            yield
+        if tp.active:
+            yield ("all_reduce", x2)
+        for b0 in range(0, B, MB):
+            nb = min(MB, B - b0)
+            if b0 == 0:
+                self._pf(w["down"], cap_mb=1.5 * cap)      # gate/up pulls the head of down_proj
+            cabi.check(L.pg_decode_gateup(ptr(self.g[b0:]), ptr(x2[b0:]), ptr(w["ln2"]), ptr(w["gu"]), nb, d.D,
+                                          F_l, d.eps, None, None, dt, st), "gateup")
+            yield
+            if b0 == 0:
+                self._pf(nxt, cap_mb=1.5 * cap)            # down_proj pulls the next layer's qkv / lm_head
+            cabi.check(L.pg_gemv_res(ptr(x[b0:]), ptr(self.g[b0:]), ptr(w["down"]),
+                                     ptr(x2[b0:]) if tp.rank == 0 else None, nb, d.D, F_l, None, dt, st), "down_proj")
+            yield
+        if tp.active:
+            yield ("all_reduce", x)
+
+    def _step_gemv_gen(self, kv: PagedKV, sample: Optional[tuple], advance: bool):
+        eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
+        B, dt, MB = self.B, self.eng.dt, cabi.MAX_DECODE_BATCH
+        tp = eng.tp
+        fab = self._fabric()
+        stride = 2 * d.L + 2
+        if fab is not None:
+            cabi.check(L.pg_tp_begin_step(ptr(fab.epoch), st), "tp_begin_step")
+            yield
         cabi.check(L.pg_embed_merge(ptr(self.x), ptr(self.ids), ptr(eng.emb), None, B, d.D, d.V,
                                     d.image_token_index, d.pad_token_id, 0, eng.img_div, eng.normalizer,
                                     ptr(eng.err_flag), dt, st), "embed")
-        scale_div = float(math.sqrt(d.hd))
-        MB = cabi.MAX_DECODE_BATCH
-        x, x2 = self.x, self.x2
-        tp, nq, F_l = eng.tp, eng.nq_l, eng.F_l
-        zero_res = None
-        for li, w in enumerate(eng.t_layers):
-            kp, vp = eng.k_pool[li], eng.v_pool[li]
-            nxt = eng.t_layers[li + 1]["qkv"] if li + 1 < len(eng.t_layers) else eng.lm_head
-            self._pf(w["o"])                                   # qkv pulls o_proj's weights
-            for b0 in range(0, B, MB):
-                nb = min(MB, B - b0)
-                cabi.check(L.pg_decode_qkv(ptr(self.q[b0:]), ptr(x[b0:]), ptr(w["ln1"]), ptr(w["qkv"]), ptr(eng.inv_freq),
-                                           ptr(self.pos[b0:]), ptr(kp), ptr(vp), ptr(kv.page_table[b0:]), kv.max_pages,
-                                           eng.page_size, ptr(kv.kv_len[b0:]), nb, d.D, nq, d.nkv, d.hd, d.eps,
-                                           d.max_pos, dt, st), "decode_qkv")
-            self._pf(w["gu"])                                  # attention pulls the head of gate/up
-            cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
-                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, nq, d.nkv, d.hd,
-                                             scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
-                       "decode_attention")
-            for b0 in range(0, B, MB):
-                nb = min(MB, B - b0)
-                if b0 == 0:
-                    self._pf(w["gu"], start_mb=cap)            # o_proj pulls the next slice of gate/up
-                # tensor parallel: only rank 0 adds the residual, so it enters the all-reduced sum once
-                cabi.check(L.pg_gemv_res(ptr(x2[b0:]), ptr(self.att[b0:]), ptr(w["o"]),
-                                         ptr(x[b0:]) if tp.rank == 0 else None, nb, d.D, nq * d.hd, dt, st), "o_proj")
-            tp.all_reduce(x2)
-            for b0 in range(0, B, MB):
-                nb = min(MB, B - b0)
-                if b0 == 0:
-                    self._pf(w["down"], cap_mb=1.5 * cap)      # gate/up pulls the head of down_proj
-                cabi.check(L.pg_decode_gateup(ptr(self.g[b0:]), ptr(x2[b0:]), ptr(w["ln2"]), ptr(w["gu"]), nb, d.D,
-                                              F_l, d.eps, dt, st), "gateup")
-                if b0 == 0:
-                    self._pf(nxt, cap_mb=1.5 * cap)            # down_proj pulls the next layer's qkv / lm_head
-                cabi.check(L.pg_gemv_res(ptr(x[b0:]), ptr(self.g[b0:]), ptr(w["down"]),
-                                         ptr(x2[b0:]) if tp.rank == 0 else None, nb, d.D, F_l, dt, st), "down_proj")
-            tp.all_reduce(x)
+        yield
+        for li in range(len(eng.t_layers)):
+            yield from self.layer_gemv_gen(li, kv, fab, first=li == 0)
         self._pf(eng.t_layers[0]["qkv"])                       # lm_head pulls layer 0 for the next step
+        ex_last = fab.x(2 * d.L, stride) if fab is not None else None
+        xin = self.x2 if fab is not None else self.x
         for b0 in range(0, B, MB):
             nb = min(MB, B - b0)
-            cabi.check(L.pg_decode_lmhead(ptr(self.local_logits[b0:]), ptr(x[b0:]), ptr(eng.final_norm), ptr(eng.lm_head),
-                                          nb, d.D, eng.V_l, d.eps, ptr(self.keys[b0:]), dt, st), "lm_head")
+            cabi.check(L.pg_decode_lmhead(ptr(self.local_logits[b0:]), ptr(xin[b0:]), ptr(eng.final_norm), ptr(eng.lm_head),
+                                          nb, d.D, eng.V_l, d.eps, ptr(self.keys[b0:]), exref(ex_last),
+                                          ptr(self.x[b0:]) if fab is not None else None, dt, st), "lm_head")
+            yield
+        yield from self._finish_gen(kv, sample, advance, fab)
+
+    def _finish_gen(self, kv: PagedKV, sample: Optional[tuple], advance: bool, fab):
+        """Token selection + bookkeeping at the end of a step.  self.keys holds this rank's packed (value, local index)
+        argmax keys, self.local_logits its vocabulary shard (the whole vocabulary when not tensor parallel)."""
+        eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
+        B, tp = self.B, self.eng.tp
+        stride = 2 * d.L + 2
+        keys_ex = None
         tp_token = None
         if tp.active:
-            # vocab-sharded lm_head: gather the per-rank (max, index) pairs; full logits only on request
-            tp.all_gather(self.gather_keys, self.keys)
-            tp_token = combine_argmax_keys(self.gather_keys, eng.V_l)
-            if self.want_full_logits or sample is not None:
-                tp.all_gather(self.gather_logits, self.local_logits)
+            if self.want_full_logits or sample is not None:   # vocab shards -> full rows (API parity / sampling)
+                yield ("all_gather", self.gather_logits, self.local_logits)
                 self.logits.view(B, tp.size, eng.V_l).copy_(self.gather_logits.permute(1, 0, 2))
+                yield
+            if sample is None:
+                if fab is not None and advance:
+                    # (max, index) pairs travel through the key exchange; pg_step_advance picks the winner
+                    keys_ex = fab.keys(2 * d.L + 1, stride)
+                    cabi.check(L.pg_tp_keys_push(ptr(self.keys), B, eng.V_l, exref(keys_ex), st), "tp_keys_push")
+                    yield
+                else:
+                    yield ("all_gather", self.gather_keys, self.keys)
+                    tp_token = combine_argmax_keys(self.gather_keys, eng.V_l)
         sampled = None
         if sample is not None:
             temperature, top_p, seed = sample
@@ -616,59 +743,113 @@ class DecodeState:
             cabi.check(L.pg_top_p_sample(ptr(self.sampled), ptr(self.logits), ptr(self.probs), B, d.V,
                                          float(temperature), float(top_p), int(seed), ptr(self.step), None, st),
                        "top_p")
+            yield
             sampled = self.sampled
         elif tp_token is not None:
             self.sampled.copy_(tp_token)
             sampled = self.sampled
         if advance:
             cabi.check(L.pg_step_advance(ptr(self.ids), ptr(self.history), self.max_hist, ptr(self.step),
-                                         ptr(self.keys), ptr(sampled), ptr(kv.kv_len), ptr(self.pos), B, st),
-                       "step_advance")
+                                         ptr(self.keys), ptr(sampled), ptr(kv.kv_len), ptr(self.pos), B,
+                                         exref(keys_ex), st), "step_advance")
+            yield
 
-    def _launch_step_batched(self, kv: PagedKV, sample: Optional[tuple], advance: bool) -> None:
+    def _step_batched_gen(self, kv: PagedKV, sample: Optional[tuple], advance: bool):
         """Decode step for batches above the GEMV tile (BASELINE configs[3]: batch 32): the projections run as
         skinny GEMMs (tcgen05 for 16-bit dtypes: weights stream through TMA once for the whole batch), attention
-        stays the cluster kernel.  Same rounding points as the GEMV path; capturable (static buffers)."""
+        stays the cluster kernel.  Same rounding points as the GEMV path; capturable (static buffers).
+        Tensor parallel: the o_proj / down_proj GEMMs leave fp32 partials in local memory, pg_tp_push hands them to
+        every rank and pg_rmsnorm_reduce (sum + residual + RMSNorm) replaces the all-reduce and the norm launch."""
         eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
         B, dt = self.B, self.eng.dt
+        tp, nq, F_l = eng.tp, eng.nq_l, eng.F_l
+        fab = self._fabric()
+        stride = 2 * d.L + 2
         if not hasattr(self, "bn"):
             self.bn = eng._new(B, d.D)
-            self.bqkv = eng._new(B, (d.nq + 2 * d.nkv) * d.hd)
+            self.bqkv = eng._new(B, (nq + 2 * d.nkv) * d.hd)
             self.bh = eng._new(B, d.D)
+            self.part = eng._new(B, d.D, dtype=torch.float32) if tp.active else None
+        if fab is not None:
+            cabi.check(L.pg_tp_begin_step(ptr(fab.epoch), st), "tp_begin_step")
+            yield
         cabi.check(L.pg_embed_merge(ptr(self.x), ptr(self.ids), ptr(eng.emb), None, B, d.D, d.V,
                                     d.image_token_index, d.pad_token_id, 0, eng.img_div, eng.normalizer,
                                     ptr(eng.err_flag), dt, st), "embed")
+        yield
         scale_div = float(math.sqrt(d.hd))
         x, x2, n = self.x, self.x2, self.bn
+        res_epi = cabi.EPI_RES if tp.rank == 0 else cabi.EPI_NONE
+
+        def reduce_norm(out, x_out, x_in, w_norm, index):
+            ex = fab.x(index, stride)
+            cabi.check(L.pg_rmsnorm_reduce(ptr(out), ptr(x_out), ptr(x_in), ptr(w_norm), B, d.D, d.eps, exref(ex), dt, st),
+                       "rmsnorm_reduce")
+
+        def partial_push(a, w_mat, index):
+            eng._gemm(self.part, a, w_mat, out_f32=True)
+            cabi.check(L.pg_tp_push(ptr(self.part), B * d.D, exref(fab.x(index, stride)), st), "tp_push")
+
         for li, w in enumerate(eng.t_layers):
             kp, vp = eng.k_pool[li], eng.v_pool[li]
-            cabi.check(L.pg_rmsnorm(ptr(n), ptr(x), ptr(w["ln1"]), B, d.D, d.eps, dt, st), "rmsnorm")
+            if fab is not None and li > 0:
+                reduce_norm(n, x, x2, w["ln1"], 2 * li)                 # x = x2 + sum(down partials of layer li-1)
+            else:
+                cabi.check(L.pg_rmsnorm(ptr(n), ptr(x), ptr(w["ln1"]), B, d.D, d.eps, dt, st), "rmsnorm")
+            yield
             eng._gemm(self.bqkv, n, w["qkv"])
+            yield
             cabi.check(L.pg_rope_append(ptr(self.q), ptr(self.bqkv), ptr(eng.inv_freq), ptr(self.pos), ptr(kp), ptr(vp),
-                                        ptr(kv.page_table), kv.max_pages, eng.page_size, ptr(kv.kv_len), B, 1, d.nq, d.nkv,
+                                        ptr(kv.page_table), kv.max_pages, eng.page_size, ptr(kv.kv_len), B, 1, nq, d.nkv,
                                         d.hd, d.max_pos, dt, st), "rope_append")
+            yield
             cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
-                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, d.nq, d.nkv, d.hd,
+                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, nq, d.nkv, d.hd,
                                              scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
                        "decode_attention")
-            eng._gemm(x2, self.att, w["o"], None, x, cabi.EPI_RES)
-            cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), B, d.D, d.eps, dt, st), "rmsnorm")
+            yield
+            if fab is not None:
+                partial_push(self.att, w["o"], 2 * li + 1)
+                yield
+                reduce_norm(n, x2, x, w["ln2"], 2 * li + 1)             # x2 = x + sum(o_proj partials)
+                yield
+            else:
+                eng._gemm(x2, self.att, w["o"], None, x if tp.rank == 0 else None, res_epi)
+                yield
+                if tp.active:
+                    yield ("all_reduce", x2)
+                cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), B, d.D, d.eps, dt, st), "rmsnorm")
+                yield
             eng._gemm(self.g, n, w["gu"], None, None, cabi.EPI_GEGLU)
-            eng._gemm(x, self.g, w["down"], None, x2, cabi.EPI_RES)
-        cabi.check(L.pg_rmsnorm(ptr(self.bh), ptr(x), ptr(eng.final_norm), B, d.D, d.eps, dt, st), "final norm")
-        eng._gemm(self.logits, self.bh, eng.lm_head, out_f32=True)
-        if sample is not None:
-            temperature, top_p, seed = sample
-            if self.probs is None:
-                self.probs = torch.empty_like(self.logits)
-            cabi.check(L.pg_top_p_sample(ptr(self.sampled), ptr(self.logits), ptr(self.probs), B, d.V,
-                                         float(temperature), float(top_p), int(seed), ptr(self.step), None, st), "top_p")
+            yield
+            if fab is not None:
+                partial_push(self.g, w["down"], 2 * li + 2)
+                yield
+            else:
+                eng._gemm(x, self.g, w["down"], None, x2 if tp.rank == 0 else None, res_epi)
+                yield
+                if tp.active:
+                    yield ("all_reduce", x)
+        if fab is not None:
+            reduce_norm(self.bh, x, x2, eng.final_norm, 2 * d.L)
         else:
-            cabi.check(L.pg_argmax(ptr(self.sampled), ptr(self.logits), ptr(self.keys), B, d.V, st), "argmax")
-        if advance:
-            cabi.check(L.pg_step_advance(ptr(self.ids), ptr(self.history), self.max_hist, ptr(self.step),
-                                         ptr(self.keys), ptr(self.sampled), ptr(kv.kv_len), ptr(self.pos), B, st),
-                       "step_advance")
+            cabi.check(L.pg_rmsnorm(ptr(self.bh), ptr(x), ptr(eng.final_norm), B, d.D, d.eps, dt, st), "final norm")
+        yield
+        eng._gemm(self.local_logits, self.bh, eng.lm_head, out_f32=True)
+        yield
+        if sample is None:
+            # packed (value, index) keys of this rank's logits; not tensor parallel: also the token itself
+            cabi.check(L.pg_argmax(None if tp.active else ptr(self.sampled), ptr(self.local_logits), ptr(self.keys), B,
+                                   eng.V_l, st), "argmax")
+            yield
+        if not tp.active and sample is None:
+            if advance:
+                cabi.check(L.pg_step_advance(ptr(self.ids), ptr(self.history), self.max_hist, ptr(self.step),
+                                             ptr(self.keys), ptr(self.sampled), ptr(kv.kv_len), ptr(self.pos), B,
+                                             None, st), "step_advance")
+                yield
+            return
+        yield from self._finish_gen(kv, sample, advance, fab)
 
     def bind(self, kv: PagedKV, next_ids: torch.Tensor, position: int) -> None:
         """Point the step at a cache and seed ids / positions (host -> device, outside the graph)."""
@@ -687,7 +868,7 @@ class DecodeState:
             for _ in range(n_steps):
                 self.launch_step(kv, sample)
         else:
-            key = (kv.page_table.data_ptr(), kv.kv_len.data_ptr(), kv.max_pages, sample)
+            key = (kv.page_table.data_ptr(), kv.kv_len.data_ptr(), kv.max_pages, sample, self.want_full_logits)
             g = self.graphs.get(key)
             if g is None:
                 # warm up on a side stream (lazy module loading, smem attributes), undo its effects

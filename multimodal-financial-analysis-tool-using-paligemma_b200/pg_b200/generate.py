@@ -46,16 +46,16 @@ def generate(eng: PaliGemmaEngine, input_ids: torch.Tensor, pixel_values: Option
             ds = eng.decode_state(B)
             # after t generated tokens the mask length is N+t; the next token is fed at position N+t (Q3)
             ds.bind(kv, first, position=N + 1)
-            if sample is not None:
-                ds.step.fill_(1)   # RNG offset continues from the prefill draw
-                hist0 = 1
-            else:
-                hist0 = 0
+            hist0 = 1 if sample is not None else 0     # RNG offset continues from the prefill draw
             ds.step.fill_(hist0)
+            ds.want_full_logits = bool(return_last_logits)
             ds.run_steps(kv, max_new_tokens - 1, sample=sample, use_graph=use_graph)
-            out[:, 1:] = ds.history[:, hist0:hist0 + max_new_tokens - 1]
+            cols = (torch.arange(max_new_tokens - 1, device=eng.device) + hist0) % ds.max_hist   # ring buffer
+            out[:, 1:] = ds.history[:, cols]
             if return_last_logits:
+                eng.check_errors(sync=True)
                 return out, ds.logits.clone()
+        eng.check_errors(sync=True)
         return out
     finally:
         kv.release()
@@ -88,4 +88,5 @@ def _generate_uncached(eng, ids, pixel_values, max_new_tokens, sample):
         nxt = _pick(eng, logits[:, -1, :].contiguous(), sample, step=t)
         out[:, t] = nxt
         cur = torch.cat([cur, nxt[:, None]], dim=1)
+    eng.check_errors(sync=True)
     return out

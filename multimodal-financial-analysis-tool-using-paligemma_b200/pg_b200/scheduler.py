@@ -103,9 +103,9 @@ class ContinuousBatcher:
         self.ds.kv = self.kv
         self.ds.ids.fill_(1)
         self.ds.pos.fill_(1)
-        self.ds.step.zero_()      # history column / RNG offset: keeps counting across chunks (no repeated draws)
+        self.ds.step.zero_()      # RNG offset + ring index of the history buffer: monotonic, never reset
         self.ds.keys.zero_()
-        self._hist_pos = 0
+        self._hist_pos = 0        # host mirror of ds.step
         self.queue: Deque[Request] = deque()
         self.running: Dict[int, Request] = {}     # slot -> request
         self.finished: Dict[int, Request] = {}
@@ -118,6 +118,10 @@ class ContinuousBatcher:
             raise ValueError("one prompt per request: input_ids must be (1, N)")
         if max_new_tokens < 1:
             raise ValueError("max_new_tokens must be >= 1")
+        cap = self.kv.max_pages * self.eng.page_size
+        if input_ids.shape[1] + int(max_new_tokens) > cap:
+            raise ValueError(f"prompt ({input_ids.shape[1]}) + max_new_tokens ({max_new_tokens}) exceeds the slot "
+                             f"capacity of {cap} tokens (ContinuousBatcher(max_tokens=...))")
         r = Request(input_ids, pixel_values, int(max_new_tokens), eos_token_id, self._next_rid)
         self._next_rid += 1
         self.queue.append(r)
@@ -135,8 +139,12 @@ class ContinuousBatcher:
             feats = eng.encode_images(r.pixel_values.to(eng.device)) if r.pixel_values is not None else None
             logits = eng.text_forward(ids, feats, kv1, logits="last")
             from .generate import _pick
-            first = _pick(eng, logits[:, -1, :].contiguous(), self.sample, step=0)
+            # the first token's draw takes its Philox offset from the request id (never the same uniform twice)
+            first = _pick(eng, logits[:, -1, :].contiguous(), self.sample, step=((r.rid + 1) << 16) & 0x3fffffff)
             pages, kv1.pages = kv1.pages[0], [[]]          # ownership moves to the slot
+        except Exception:
+            self.queue.appendleft(r)                       # admission failed (e.g. pool exhausted): nothing is lost
+            raise
         finally:
             kv1.release()
         tok = int(first.item())
@@ -170,12 +178,11 @@ class ContinuousBatcher:
             self.kv.kv_len.index_fill_(0, idx, 0)
             self.ds.pos.index_fill_(0, idx, 1)
             self.ds.ids.index_fill_(0, idx, 1)
-        if self._hist_pos + n > self.ds.max_hist:           # wrap the history buffer
-            self.ds.step.zero_()
-            self._hist_pos = 0
         self.ds.run_steps(self.kv, n, sample=self.sample)
         self.steps_run += n
-        hist = self.ds.history[:, self._hist_pos:self._hist_pos + n].cpu()   # one read-back per chunk
+        cols = (torch.arange(n, device=self.eng.device) + self._hist_pos) % self.ds.max_hist   # ring buffer
+        hist = self.ds.history[:, cols].cpu()               # one read-back per chunk
+        self.eng.check_errors()                             # the read-back synchronised: bad ids raise here
         self._hist_pos += n
         for slot, r in list(self.running.items()):
             self.kv.host_len[slot] += n

@@ -196,6 +196,115 @@ def golden_full(dtype, tag: str, steps: int, unc_steps: int):
     np.savez_compressed(os.path.join(OUT, f"full_{tag}.npz"), **out)
 
 
+def _bits(x: torch.Tensor) -> np.ndarray:
+    """Exact bit pattern of a bf16 tensor (npz has no bf16)."""
+    return x.detach().contiguous().view(torch.int16).cpu().numpy()
+
+
+@torch.no_grad()
+def golden_full_decode_bf16(steps: int = 16, probe_step: int = 4, probe_layers=(0, 9, 17)):
+    """Full-size bf16 CACHED DECODE, the configuration bench.py times: the reference model in bf16 decodes `steps`
+    greedy tokens; every step's logits are summarised (top-8 + a 1/31 subsample) and at `probe_step` the input and
+    output hidden state of a few decoder layers plus those layers' K/V caches are dumped bit-exactly, so a single
+    layer of the CUDA decode path can be checked with the reference's own inputs (no error amplification through the
+    stack).  The fp32 reference model then replays the SAME tokens (teacher forced): its logits are the truth both
+    bf16 implementations are measured against."""
+    cfg = synth.CONFIGS["paligemma-3b-pt-224"]
+    ids = synth.synth_prompt_ids(cfg)
+    pix = synth.synth_pixels(cfg)
+    out = {}
+    m = build_reference_model(cfg, torch.bfloat16, patched=False)
+    layers = m.language_model.model.layers
+    grabbed = {}
+
+    def pre_hook(k):
+        def fn(mod, args, kwargs):
+            if grabbed.get("on"):
+                hs = kwargs.get("hidden_states", args[0] if args else None)
+                grabbed[f"in_{k}"] = hs.detach().clone()
+                kvc = kwargs["kv_cache"]
+                grabbed[f"k_{k}"] = kvc.key_cache[k].detach().clone()
+                grabbed[f"v_{k}"] = kvc.value_cache[k].detach().clone()
+        return fn
+
+    def post_hook(k):
+        def fn(mod, args, kwargs, output):
+            if grabbed.get("on"):
+                grabbed[f"out_{k}"] = (output[0] if isinstance(output, tuple) else output).detach().clone()
+        return fn
+
+    for k in probe_layers:
+        layers[k].register_forward_pre_hook(pre_hook(k), with_kwargs=True)
+        layers[k].register_forward_hook(post_hook(k), with_kwargs=True)
+    mask = torch.ones_like(ids)
+    kv = ref_gemma.KVCache()
+    t0 = time.time()
+    o = m(input_ids=ids, pixel_values=pix.to(torch.bfloat16), attention_mask=mask, kv_cache=kv)
+    lg = o["logits"][:, -1, :]
+    toks, logits = [torch.argmax(lg, -1, keepdim=True)], [lg]
+    for s in range(steps):
+        mask = torch.cat([mask, torch.ones((1, 1))], dim=-1)
+        grabbed["on"] = s == probe_step
+        o = m(input_ids=toks[-1], pixel_values=None, attention_mask=mask, kv_cache=kv)
+        grabbed["on"] = False
+        lg = o["logits"][:, -1, :]
+        logits.append(lg)
+        toks.append(torch.argmax(lg, -1, keepdim=True))
+    print(f"bf16 decode {steps} steps {time.time() - t0:.0f}s tokens {torch.cat(toks, -1).tolist()}", flush=True)
+    lg = torch.stack(logits, 1)                       # (1, steps+1, V): index 0 = prefill, s+1 = cached step s
+    out["tokens"] = _np(torch.cat(toks, -1))          # tokens[:, s] is FED at cached step s; tokens[:, s+1] is its argmax
+    out["logits_sub"] = _np(lg[:, :, ::31])
+    out["topv"], out["topi"] = topk_summary(lg)
+    out["probe_step"] = np.array(probe_step)
+    out["probe_layers"] = np.array(probe_layers)
+    out["probe_position"] = np.array(ids.shape[1] + probe_step + 1)   # attention-mask length at that step (Q3)
+    for k in probe_layers:
+        out[f"in_{k}"], out[f"out_{k}"] = _bits(grabbed[f"in_{k}"]), _bits(grabbed[f"out_{k}"])
+        out[f"k_{k}"], out[f"v_{k}"] = _bits(grabbed[f"k_{k}"]), _bits(grabbed[f"v_{k}"])
+    del m, kv
+    # fp32 truth, teacher forced with the bf16 run's tokens
+    m32 = build_reference_model(cfg, torch.float32, patched=False)
+    mask = torch.ones_like(ids)
+    kv = ref_gemma.KVCache()
+    o = m32(input_ids=ids, pixel_values=pix, attention_mask=mask, kv_cache=kv)
+    truth = [o["logits"][:, -1, :]]
+    for s in range(steps):
+        mask = torch.cat([mask, torch.ones((1, 1))], dim=-1)
+        o = m32(input_ids=toks[s], pixel_values=None, attention_mask=mask, kv_cache=kv)
+        truth.append(o["logits"][:, -1, :])
+    tr = torch.stack(truth, 1)
+    out["truth_logits_sub"] = _np(tr[:, :, ::31])
+    out["truth_at_topi"] = _np(torch.gather(tr, -1, torch.from_numpy(out["topi"])))
+    out["ref_noise_rms"] = np.array(float((lg.float() - tr).pow(2).mean().sqrt()))
+    out["logit_rms"] = np.array(float(tr.pow(2).mean().sqrt()))
+    print(f"reference bf16 vs fp32 truth: rms {float(out['ref_noise_rms']):.4f} (logit rms {float(out['logit_rms']):.3f})", flush=True)
+    np.savez_compressed(os.path.join(OUT, "full_bf16_decode.npz"), **out)
+
+
+@torch.no_grad()
+def golden_vision_batch_bf16(batch: int = 64):
+    """BASELINE configs[2]: SigLIP tower + projector over a batch of 64 synthetic images in bf16 through the
+    reference modules; a strided subsample of every image's projected features (and the fp32 reference run of the
+    first 4 images as the truth for the noise yardstick)."""
+    cfg = synth.CONFIGS["paligemma-3b-pt-224"]
+    pix = synth.synth_pixels(cfg, batch=batch)
+    out = {}
+    m = build_reference_model(cfg, torch.bfloat16, patched=False)
+    t0 = time.time()
+    feats = torch.cat([m.vision_tower(pix[i:i + 8].to(torch.bfloat16)) for i in range(0, batch, 8)])
+    proj = m.multi_modal_projector(feats)
+    print(f"vision bf16 batch {batch}: {time.time() - t0:.0f}s", flush=True)
+    out["features_sub"] = _np(feats[:, ::17, ::13])
+    out["projected_sub"] = _np(proj[:, ::17, ::13])
+    del m
+    m32 = build_reference_model(cfg, torch.float32, patched=False)
+    f32 = m32.vision_tower(pix[:4])
+    p32 = m32.multi_modal_projector(f32)
+    out["truth_features_sub"] = _np(f32[:, ::17, ::13])
+    out["truth_projected_sub"] = _np(p32[:, ::17, ::13])
+    np.savez_compressed(os.path.join(OUT, "vision_b64_bf16.npz"), **out)
+
+
 def golden_processor():
     """The reference's own PaliGemmaProcessor (processing_paligemma.py:52-117) on a synthetic RGB image and the
     stub tokenizer: pins resize / rescale / normalise / prompt construction of the drop-in processor."""
@@ -227,3 +336,7 @@ if __name__ == "__main__":
         golden_full(torch.float32, "fp32", steps=32, unc_steps=4)
     if "full_bf16" in what:
         golden_full(torch.bfloat16, "bf16", steps=32, unc_steps=2)
+    if "full_bf16_decode" in what:
+        golden_full_decode_bf16()
+    if "vision_b64" in what:
+        golden_vision_batch_bf16()

@@ -253,7 +253,7 @@ def test_decode_layer_kernels(dtype, B, D, nq, hd, F_):
     wqkv = dev(torch.cat([wq, wk, wv], 0))
     cabi.check(cabi.lib().pg_decode_qkv(qo.data_ptr(), dev(x).data_ptr(), dev(lnw).data_ptr(), wqkv.data_ptr(),
                                         inv.data_ptr(), dev(pos).data_ptr(), kp.data_ptr(), vp.data_ptr(), pt.data_ptr(),
-                                        npg, page, kvl.data_ptr(), B, D, nq, nkv, hd, 1e-6, 8192,
+                                        npg, page, kvl.data_ptr(), B, D, nq, nkv, hd, 1e-6, 8192, None, None,
                                         cabi.DTYPE_CODE[dtype], st()))
     close(qo, q_ref.transpose(1, 2).reshape(B, nq * hd), dtype)
     got_k = torch.stack([kp[pt[b, T0 // page].item(), T0 % page] for b in range(B)])
@@ -266,13 +266,13 @@ def test_decode_layer_kernels(dtype, B, D, nq, hd, F_):
         w = gen(D, K, seed=8, scale=1 / math.sqrt(K), dtype=dtype)
         out = torch.empty((B, D), dtype=dtype, device="cuda")
         cabi.check(cabi.lib().pg_gemv_res(out.data_ptr(), dev(a).data_ptr(), dev(w).data_ptr(), dev(x).data_ptr(), B, D, K,
-                                          cabi.DTYPE_CODE[dtype], st()))
+                                          None, cabi.DTYPE_CODE[dtype], st()))
         close(out, x + F.linear(a, w), dtype)
     # gate/up + GeGLU with the post-attention norm fused
     wg, wu = gen(F_, D, seed=10, scale=s, dtype=dtype), gen(F_, D, seed=11, scale=s, dtype=dtype)
     out = torch.empty((B, F_), dtype=dtype, device="cuda")
     cabi.check(cabi.lib().pg_decode_gateup(out.data_ptr(), dev(x).data_ptr(), dev(lnw).data_ptr(),
-                                           dev(torch.cat([wg, wu], 0)).data_ptr(), B, D, F_, 1e-6,
+                                           dev(torch.cat([wg, wu], 0)).data_ptr(), B, D, F_, 1e-6, None, None,
                                            cabi.DTYPE_CODE[dtype], st()))
     close(out, F.gelu(F.linear(h, wg), approximate="tanh") * F.linear(h, wu), dtype)
 
@@ -286,7 +286,7 @@ def test_lmhead_argmax_and_step_advance(dtype, B, D, V):
     logits = torch.empty((B, V), dtype=torch.float32, device="cuda")
     keys = torch.zeros(B, dtype=torch.int64, device="cuda")
     cabi.check(cabi.lib().pg_decode_lmhead(logits.data_ptr(), dev(x).data_ptr(), dev(lnw).data_ptr(), dev(emb).data_ptr(),
-                                           B, D, V, 1e-6, keys.data_ptr(), cabi.DTYPE_CODE[dtype], st()))
+                                           B, D, V, 1e-6, keys.data_ptr(), None, None, cabi.DTYPE_CODE[dtype], st()))
     close(logits, want, dtype)
     ids = torch.zeros(B, dtype=torch.int64, device="cuda")
     hist = torch.zeros((B, 4), dtype=torch.int64, device="cuda")
@@ -294,7 +294,7 @@ def test_lmhead_argmax_and_step_advance(dtype, B, D, V):
     kvl = torch.full((B,), 9, dtype=torch.int32, device="cuda")
     pos = torch.full((B,), 11, dtype=torch.int32, device="cuda")
     cabi.check(cabi.lib().pg_step_advance(ids.data_ptr(), hist.data_ptr(), 4, step.data_ptr(), keys.data_ptr(), None,
-                                          kvl.data_ptr(), pos.data_ptr(), B, st()))
+                                          kvl.data_ptr(), pos.data_ptr(), B, None, st()))
     # the kernel's own logits decide (ties -> lowest index, as torch.argmax on the same values)
     assert ids.cpu().tolist() == torch.argmax(logits.cpu(), dim=-1).tolist()
     assert hist[:, 2].cpu().tolist() == ids.cpu().tolist() and int(step.item()) == 3

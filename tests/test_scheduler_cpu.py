@@ -25,7 +25,7 @@ class StubDecodeState:
     def run_steps(self, kv, n, sample=None):
         self.calls.append(n)
         for _ in range(n):
-            col = int(self.step.item())
+            col = int(self.step.item()) % self.max_hist      # ring buffer, like step_advance_kernel
             for b in range(self.B):
                 L, pos = int(kv.kv_len[b]), int(self.pos[b])
                 # an active row must own a real (non-parking) page for the entry it is about to write
@@ -67,6 +67,9 @@ class StubEngine:
 
     def encode_images(self, pixels):
         return None
+
+    def check_errors(self, sync=False):
+        pass
 
     def text_forward(self, ids, feats, kv, logits="last"):
         N = ids.shape[1]
@@ -131,9 +134,31 @@ def test_scheduler_eos_and_capacity(monkeypatch):
     # a sequence that outgrows its slot is refused loudly
     cb = S.ContinuousBatcher(eng, slots=1, max_tokens=8, chunk=4)
     cb.kv.assign = lambda slot, pages, length, f=cb.kv.assign: (eng.slot_owner.__setitem__(slot, (eng.prefills[-1], length)), f(slot, pages, length))[1]
-    cb.submit(torch.arange(1, 7, dtype=torch.int64)[None], None, 10)
     try:
-        cb.run()
+        cb.submit(torch.arange(1, 7, dtype=torch.int64)[None], None, 10)     # 6 + 10 > 8: refused at submit()
         raise AssertionError("expected a capacity error")
-    except RuntimeError as e:
+    except ValueError as e:
         assert "capacity" in str(e)
+    assert not cb.queue
+
+
+def test_scheduler_history_ring_wraps(monkeypatch):
+    """More decode steps than the history buffer holds (the stub's is 64 columns): the step counter keeps counting
+    (it is also the sampler's RNG offset), the history is read as a ring, tokens stay right."""
+    _patch_pick(monkeypatch)
+    eng = StubEngine(pages=256)
+    cb = S.ContinuousBatcher(eng, slots=2, max_tokens=256, chunk=5)
+    orig_assign = cb.kv.assign
+    def assign(slot, pages, length):
+        eng.slot_owner[slot] = (eng.prefills[-1], length)
+        orig_assign(slot, pages, length)
+    cb.kv.assign = assign
+    prompts = [torch.arange(1, 1 + n, dtype=torch.int64)[None] for n in (4, 6, 5)]
+    budgets = [150, 90, 70]
+    rids = [cb.submit(p, None, b) for p, b in zip(prompts, budgets)]
+    done = cb.run()
+    for rid, p, b in zip(rids, prompts, budgets):
+        assert done[rid].tokens == [_stream(int(p.sum()), t) for t in range(b)]
+    assert int(cb.ds.step.item()) > cb.ds.max_hist                # wrapped at least once, never reset
+    cb.close()
+    assert sorted(eng._free) == list(range(256))

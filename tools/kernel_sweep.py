@@ -74,7 +74,7 @@ def main():
         for li, w in enumerate(eng.t_layers):
             L.pg_decode_qkv(ds.q.data_ptr(), ds.x.data_ptr(), w["ln1"].data_ptr(), w["qkv"].data_ptr(), eng.inv_freq.data_ptr(),
                             ds.pos.data_ptr(), eng.k_pool[li].data_ptr(), eng.v_pool[li].data_ptr(), kv.page_table.data_ptr(),
-                            kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), B, d.D, d.nq, d.nkv, d.hd, d.eps, d.max_pos, dt, st)
+                            kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), B, d.D, d.nq, d.nkv, d.hd, d.eps, d.max_pos, None, None, dt, st)
     rec("qkv", qkv, e * (d.nq + 2 * d.nkv) * d.hd * d.D)
 
     def attn():
@@ -86,22 +86,22 @@ def main():
 
     def oproj():
         for li, w in enumerate(eng.t_layers):
-            L.pg_gemv_res(ds.x2.data_ptr(), ds.att.data_ptr(), w["o"].data_ptr(), ds.x.data_ptr(), B, d.D, d.nq * d.hd, dt, st)
+            L.pg_gemv_res(ds.x2.data_ptr(), ds.att.data_ptr(), w["o"].data_ptr(), ds.x.data_ptr(), B, d.D, d.nq * d.hd, None, dt, st)
     rec("o_proj", oproj, e * d.D * d.nq * d.hd)
 
     def gateup():
         for li, w in enumerate(eng.t_layers):
-            L.pg_decode_gateup(ds.g.data_ptr(), ds.x2.data_ptr(), w["ln2"].data_ptr(), w["gu"].data_ptr(), B, d.D, d.F, d.eps, dt, st)
+            L.pg_decode_gateup(ds.g.data_ptr(), ds.x2.data_ptr(), w["ln2"].data_ptr(), w["gu"].data_ptr(), B, d.D, d.F, d.eps, None, None, dt, st)
     rec("gateup", gateup, e * 2 * d.F * d.D)
 
     def down():
         for li, w in enumerate(eng.t_layers):
-            L.pg_gemv_res(ds.x.data_ptr(), ds.g.data_ptr(), w["down"].data_ptr(), ds.x2.data_ptr(), B, d.D, d.F, dt, st)
+            L.pg_gemv_res(ds.x.data_ptr(), ds.g.data_ptr(), w["down"].data_ptr(), ds.x2.data_ptr(), B, d.D, d.F, None, dt, st)
     rec("down", down, e * d.F * d.D)
 
     def lmhead():
         L.pg_decode_lmhead(ds.logits.data_ptr(), ds.x.data_ptr(), eng.final_norm.data_ptr(), eng.lm_head.data_ptr(), B, d.D, d.V,
-                           d.eps, ds.keys.data_ptr(), dt, st)
+                           d.eps, ds.keys.data_ptr(), None, None, dt, st)
     med, mn = timeit(lmhead, 1)
     res["lm_head"] = {"us": round(med, 2), "min_us": round(mn, 2), "GBps": round(e * d.V * d.D / med / 1e3, 1)}
 
