@@ -106,22 +106,23 @@ class TP:
         self.rank, self.size, self.group = rank, size, group
         self.fabric = fabric
         self.emulated = emulated          # collectives are performed by a LockstepGroup, not torch.distributed
-        self._fabric_tried = fabric is not None
 
     @property
     def active(self) -> bool:
         return self.size > 1
 
-    def ensure_fabric(self, D: int, device) -> Optional[Fabric]:
-        """Create the peer-memory exchange on first use (PG_TP_EXCHANGE=nccl keeps the collective path, for A/B runs)."""
+    def make_fabric(self, D: int, device) -> Optional[Fabric]:
+        """The exchange of ONE engine (its own buffers and step counter: sequence numbers of two models never mix).
+        Collective: every rank builds its engines in the same order.  PG_TP_EXCHANGE=nccl keeps the collective path
+        (A/B runs); emulated ranks get their fabric from the test (Fabric.emulated)."""
         import os
-        if self._fabric_tried or not self.active:
-            return self.fabric
-        self._fabric_tried = True
-        if os.environ.get("PG_TP_EXCHANGE", "peer") == "nccl" or self.size > 8 or self.emulated:
+        if not self.active:
             return None
-        self.fabric = Fabric.symmetric(self.rank, self.size, D, device)
-        return self.fabric
+        if self.emulated:
+            return self.fabric
+        if os.environ.get("PG_TP_EXCHANGE", "peer") == "nccl" or self.size > 8:
+            return None
+        return Fabric.symmetric(self.rank, self.size, D, device)
 
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.size > 1:

@@ -119,7 +119,7 @@ class PaliGemmaEngine:
 
     def __init__(self, config, weights: Mapping[str, torch.Tensor], *, device=None, dtype=None,
                  page_size: int = 64, kv_pool_tokens: int = 65536, gemm_impl: int = 0,
-                 adopt=None, tp=None):
+                 adopt=None, tp=None, batched_min: Optional[int] = None):
         cabi.lib()  # fail now if the CUDA library is missing
         self.dims = d = Dims.from_config(config)
         self.tp = tp if tp is not None else TP()
@@ -139,6 +139,8 @@ class PaliGemmaEngine:
         # rows from which the decode step / last-position lm_head use the tensor-core GEMMs instead of the GEMV kernels
         # (fp32 verification mode has no tensor-core path: GEMV up to its 8-row limit)
         self.batched_min = cabi.BATCHED_DECODE_MIN if self.dtype != torch.float32 else cabi.MAX_DECODE_BATCH + 1
+        if batched_min is not None:     # tests: drive the batched step's launch sequence in fp32 (SIMT GEMMs) too
+            self.batched_min = int(batched_min)
         self._op_timing = os.environ.get("PG_OP_TIMING", "0") == "1"
         self._vision_graphs_on = os.environ.get("PG_VISION_GRAPH", "1") != "0"
         self._vision_graphs: Dict[tuple, tuple] = {}
@@ -168,7 +170,7 @@ class PaliGemmaEngine:
         self.max_splits = 32
         self._decode_states: Dict[tuple, "DecodeState"] = {}
         # tensor parallel: the peer-memory exchange the decode kernels use instead of collectives (dist.Fabric)
-        self.fabric = self.tp.ensure_fabric(d.D, self.device) if self.tp.active else None
+        self.fabric = self.tp.make_fabric(d.D, self.device)
         if self.fabric is not None and 2 * d.L + 2 > 4096:
             raise ValueError("too many layers for the exchange sequence numbering")
 
@@ -539,8 +541,8 @@ class PaliGemmaEngine:
         decode path reports at the next call (like the deferred mask check)."""
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
-        if self._err_np[0] != 0 or (self.tp.fabric is not None and self.tp.fabric.lost_peer()):
-            lost = self.tp.fabric is not None and self.tp.fabric.lost_peer()
+        if self._err_np[0] != 0 or (self.fabric is not None and self.fabric.lost_peer()):
+            lost = self.fabric is not None and self.fabric.lost_peer()
             self._err_np[0] = 0
             if lost:
                 raise RuntimeError("tensor-parallel exchange timed out waiting for a peer rank")
@@ -754,6 +756,76 @@ class DecodeState:
                                          exref(keys_ex), st), "step_advance")
             yield
 
+    def _batched_buffers(self):
+        eng, d = self.eng, self.eng.dims
+        if not hasattr(self, "bn"):
+            self.bn = eng._new(self.B, d.D)
+            self.bqkv = eng._new(self.B, (eng.nq_l + 2 * d.nkv) * d.hd)
+            self.bh = eng._new(self.B, d.D)
+            self.part = eng._new(self.B, d.D, dtype=torch.float32) if eng.tp.active else None
+
+    def _reduce_norm(self, fab, out, x_out, x_in, w_norm, index):
+        d = self.eng.dims
+        ex = fab.x(index, 2 * d.L + 2)
+        cabi.check(cabi.lib().pg_rmsnorm_reduce(ptr(out), ptr(x_out), ptr(x_in), ptr(w_norm), self.B, d.D, d.eps, exref(ex),
+                                                self.eng.dt, cabi.stream()), "rmsnorm_reduce")
+
+    def _partial_push(self, fab, a, w_mat, index):
+        d = self.eng.dims
+        self.eng._gemm(self.part, a, w_mat, out_f32=True)
+        cabi.check(cabi.lib().pg_tp_push(ptr(self.part), self.B * d.D, exref(fab.x(index, 2 * d.L + 2)), cabi.stream()),
+                   "tp_push")
+
+    def layer_batched_gen(self, li: int, kv: PagedKV, fab, first: bool):
+        """Decoder layer `li` of the tensor-core step (same stream conventions as layer_gemv_gen)."""
+        eng, d, L, st = self.eng, self.eng.dims, cabi.lib(), cabi.stream()
+        B, dt = self.B, self.eng.dt
+        tp, nq = eng.tp, eng.nq_l
+        self._batched_buffers()
+        w = eng.t_layers[li]
+        scale_div = float(math.sqrt(d.hd))
+        x, x2, n = self.x, self.x2, self.bn
+        res_epi = cabi.EPI_RES if tp.rank == 0 else cabi.EPI_NONE
+        kp, vp = eng.k_pool[li], eng.v_pool[li]
+        if fab is not None and not first:
+            self._reduce_norm(fab, n, x, x2, w["ln1"], 2 * li)          # x = x2 + sum(down partials of layer li-1)
+        else:
+            cabi.check(L.pg_rmsnorm(ptr(n), ptr(x), ptr(w["ln1"]), B, d.D, d.eps, dt, st), "rmsnorm")
+        yield
+        eng._gemm(self.bqkv, n, w["qkv"])
+        yield
+        cabi.check(L.pg_rope_append(ptr(self.q), ptr(self.bqkv), ptr(eng.inv_freq), ptr(self.pos), ptr(kp), ptr(vp),
+                                    ptr(kv.page_table), kv.max_pages, eng.page_size, ptr(kv.kv_len), B, 1, nq, d.nkv,
+                                    d.hd, d.max_pos, dt, st), "rope_append")
+        yield
+        cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
+                                         kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, nq, d.nkv, d.hd,
+                                         scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
+                   "decode_attention")
+        yield
+        if fab is not None:
+            self._partial_push(fab, self.att, w["o"], 2 * li + 1)
+            yield
+            self._reduce_norm(fab, n, x2, x, w["ln2"], 2 * li + 1)      # x2 = x + sum(o_proj partials)
+            yield
+        else:
+            eng._gemm(x2, self.att, w["o"], None, x if tp.rank == 0 else None, res_epi)
+            yield
+            if tp.active:
+                yield ("all_reduce", x2)
+            cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), B, d.D, d.eps, dt, st), "rmsnorm")
+            yield
+        eng._gemm(self.g, n, w["gu"], None, None, cabi.EPI_GEGLU)
+        yield
+        if fab is not None:
+            self._partial_push(fab, self.g, w["down"], 2 * li + 2)
+            yield
+        else:
+            eng._gemm(x, self.g, w["down"], None, x2 if tp.rank == 0 else None, res_epi)
+            yield
+            if tp.active:
+                yield ("all_reduce", x)
+
     def _step_batched_gen(self, kv: PagedKV, sample: Optional[tuple], advance: bool):
         """Decode step for batches above the GEMV tile (BASELINE configs[3]: batch 32): the projections run as
         skinny GEMMs (tcgen05 for 16-bit dtypes: weights stream through TMA once for the whole batch), attention
@@ -765,11 +837,7 @@ class DecodeState:
         tp, nq, F_l = eng.tp, eng.nq_l, eng.F_l
         fab = self._fabric()
         stride = 2 * d.L + 2
-        if not hasattr(self, "bn"):
-            self.bn = eng._new(B, d.D)
-            self.bqkv = eng._new(B, (nq + 2 * d.nkv) * d.hd)
-            self.bh = eng._new(B, d.D)
-            self.part = eng._new(B, d.D, dtype=torch.float32) if tp.active else None
+        self._batched_buffers()
         if fab is not None:
             cabi.check(L.pg_tp_begin_step(ptr(fab.epoch), st), "tp_begin_step")
             yield
@@ -777,61 +845,11 @@ class DecodeState:
                                     d.image_token_index, d.pad_token_id, 0, eng.img_div, eng.normalizer,
                                     ptr(eng.err_flag), dt, st), "embed")
         yield
-        scale_div = float(math.sqrt(d.hd))
-        x, x2, n = self.x, self.x2, self.bn
-        res_epi = cabi.EPI_RES if tp.rank == 0 else cabi.EPI_NONE
-
-        def reduce_norm(out, x_out, x_in, w_norm, index):
-            ex = fab.x(index, stride)
-            cabi.check(L.pg_rmsnorm_reduce(ptr(out), ptr(x_out), ptr(x_in), ptr(w_norm), B, d.D, d.eps, exref(ex), dt, st),
-                       "rmsnorm_reduce")
-
-        def partial_push(a, w_mat, index):
-            eng._gemm(self.part, a, w_mat, out_f32=True)
-            cabi.check(L.pg_tp_push(ptr(self.part), B * d.D, exref(fab.x(index, stride)), st), "tp_push")
-
-        for li, w in enumerate(eng.t_layers):
-            kp, vp = eng.k_pool[li], eng.v_pool[li]
-            if fab is not None and li > 0:
-                reduce_norm(n, x, x2, w["ln1"], 2 * li)                 # x = x2 + sum(down partials of layer li-1)
-            else:
-                cabi.check(L.pg_rmsnorm(ptr(n), ptr(x), ptr(w["ln1"]), B, d.D, d.eps, dt, st), "rmsnorm")
-            yield
-            eng._gemm(self.bqkv, n, w["qkv"])
-            yield
-            cabi.check(L.pg_rope_append(ptr(self.q), ptr(self.bqkv), ptr(eng.inv_freq), ptr(self.pos), ptr(kp), ptr(vp),
-                                        ptr(kv.page_table), kv.max_pages, eng.page_size, ptr(kv.kv_len), B, 1, nq, d.nkv,
-                                        d.hd, d.max_pos, dt, st), "rope_append")
-            yield
-            cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
-                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, nq, d.nkv, d.hd,
-                                             scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
-                       "decode_attention")
-            yield
-            if fab is not None:
-                partial_push(self.att, w["o"], 2 * li + 1)
-                yield
-                reduce_norm(n, x2, x, w["ln2"], 2 * li + 1)             # x2 = x + sum(o_proj partials)
-                yield
-            else:
-                eng._gemm(x2, self.att, w["o"], None, x if tp.rank == 0 else None, res_epi)
-                yield
-                if tp.active:
-                    yield ("all_reduce", x2)
-                cabi.check(L.pg_rmsnorm(ptr(n), ptr(x2), ptr(w["ln2"]), B, d.D, d.eps, dt, st), "rmsnorm")
-                yield
-            eng._gemm(self.g, n, w["gu"], None, None, cabi.EPI_GEGLU)
-            yield
-            if fab is not None:
-                partial_push(self.g, w["down"], 2 * li + 2)
-                yield
-            else:
-                eng._gemm(x, self.g, w["down"], None, x2 if tp.rank == 0 else None, res_epi)
-                yield
-                if tp.active:
-                    yield ("all_reduce", x)
+        for li in range(len(eng.t_layers)):
+            yield from self.layer_batched_gen(li, kv, fab, first=li == 0)
+        x, x2 = self.x, self.x2
         if fab is not None:
-            reduce_norm(self.bh, x, x2, eng.final_norm, 2 * d.L)
+            self._reduce_norm(fab, self.bh, x, x2, eng.final_norm, 2 * d.L)
         else:
             cabi.check(L.pg_rmsnorm(ptr(self.bh), ptr(x), ptr(eng.final_norm), B, d.D, d.eps, dt, st), "final norm")
         yield

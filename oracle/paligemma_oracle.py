@@ -282,11 +282,13 @@ def top_p_distribution(logits: torch.Tensor, temperature: float, p: float) -> to
 
 @torch.no_grad()
 def generate_cached(sd: SD, cfg: dict, input_ids, pixel_values, max_tokens: int,
-                    patched: bool = True, refeed_prompt: bool = False, return_logits: bool = False):
+                    patched: bool = True, refeed_prompt: bool = False, return_logits: bool = False,
+                    teacher: Optional[torch.Tensor] = None):
     """Greedy cache-on loop — inference.py:50-78 (with pixel_values dropped after the first
     call as ablation_study_fixed.py:243; Q5 shows the output is unchanged).  refeed_prompt
     reproduces the ablation harness: an extra prefill before the loop (:193-199) so the
-    prompt is cached twice (Q6)."""
+    prompt is cached twice (Q6).  teacher (B, >= max_tokens-1): feed teacher[:, t] instead of the step's own argmax
+    (parity tests compare logits of reduced-precision runs on identical token streams)."""
     b, n = input_ids.shape
     mask = torch.ones((b, n), dtype=torch.int64)
     kv = OracleKV()
@@ -294,13 +296,13 @@ def generate_cached(sd: SD, cfg: dict, input_ids, pixel_values, max_tokens: int,
     if refeed_prompt:
         forward(sd, cfg, ids, pix, mask, kv, patched)
     toks, all_logits = [], []
-    for _ in range(max_tokens):
+    for t in range(max_tokens):
         logits = forward(sd, cfg, ids, pix, mask, kv, patched)[:, -1, :]
         nxt = torch.argmax(logits, dim=-1, keepdim=True)
         toks.append(nxt)
         if return_logits:
             all_logits.append(logits)
-        ids, pix = nxt, None
+        ids, pix = (nxt if teacher is None or t >= teacher.shape[1] else teacher[:, t:t + 1]), None
         mask = torch.cat([mask.to(torch.float32) if mask.dtype != torch.float32 else mask,
                           torch.ones((b, 1))], dim=-1)
     out = torch.cat(toks, dim=-1)

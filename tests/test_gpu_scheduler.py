@@ -1,9 +1,10 @@
 """Continuous batching (pg_b200/scheduler.py): requests of different prompt lengths and budgets share one decode
-graph through slot rows of a static page table; every request's tokens must equal `generate()` on that request alone
-(the reference loop of inference.py:50-78 run once per request)."""
+graph through slot rows of a static page table; every request's tokens must equal the CPU ORACLE's greedy loop on that
+request alone (the reference loop of inference.py:50-78 run once per request)."""
 import pytest
 import torch
 
+from oracle import paligemma_oracle as O
 from pg_b200 import synth
 from pg_b200.generate import generate
 from pg_b200.scheduler import ContinuousBatcher
@@ -36,7 +37,9 @@ def test_continuous_batching_equals_per_request_generation_fp32():
     model, cfg = _model("tiny", torch.float32)
     eng = model._engine_ready()
     reqs = _requests(cfg)
-    want = [generate(eng, ids.cuda(), pix.cuda(), budget).cpu()[0].tolist() for ids, pix, budget in reqs]
+    sd = synth.synth_state_dict(cfg)
+    want = [O.generate_cached(sd, cfg, ids, pix, budget, patched=True)[0].tolist() for ids, pix, budget in reqs]
+    assert want == [generate(eng, ids.cuda(), pix.cuda(), budget).cpu()[0].tolist() for ids, pix, budget in reqs]
     free_before = len(eng._free)
     cb = ContinuousBatcher(eng, slots=3, max_tokens=256, chunk=4)
     rids = [cb.submit(ids, pix, budget) for ids, pix, budget in reqs]

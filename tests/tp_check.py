@@ -10,6 +10,7 @@ import torch
 import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "multimodal-financial-analysis-tool-using-paligemma_b200"))
 from pg_b200 import synth  # noqa: E402
 from pg_b200.dist import TP  # noqa: E402
@@ -17,7 +18,6 @@ import modeling_gemma as MG  # noqa: E402
 
 
 def main():
-    os.environ.setdefault("PG_TP_ALLREDUCE", "oneshot")  # exercise the peer-memory all-reduce too (falls back to NCCL)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -54,11 +54,51 @@ def main():
             ok &= good
             print(f"[rank {rank}] {name} tp={world}: tokens {'OK' if toks == g['cached_tokens'].tolist() else toks} "
                   f"api {'OK' if [api] == g['cached_tokens'].tolist() else api} max|dlogit| {err:.2e} (tol {tol:.2e})", flush=True)
-    if tp.oneshot is not None:
-        ok &= int(tp.oneshot.err.item()) == 0
-        print(f"[rank {rank}] one-shot all-reduce used, {int(tp.oneshot.step.item())} calls, err flag {int(tp.oneshot.err.item())}", flush=True)
+    # bf16, small shapes: GEMV step (batch 2) and tensor-core step (batch 6), teacher-forced against the CPU oracle
+    from oracle import paligemma_oracle as O
+    from pg_b200.generate import generate
+    cfg = synth.CONFIGS["small"]
+    if cfg["text_config"]["num_attention_heads"] % world == 0:
+        sd32 = synth.synth_state_dict(cfg)
+        sdb = {k: v.to(torch.bfloat16) for k, v in sd32.items()}
+        model = MG.PaliGemmaForConditionalGeneration(MG.PaliGemmaConfig(**cfg), init_weights=False, tp=tp)
+        model.load_state_dict({k: v for k, v in sdb.items() if "lm_head" not in k}, strict=False)
+        model.tie_weights()
+        model = model.to("cuda").eval()
+        eng = model._engine_ready()
+        for batch in (2, 6):
+            ids = synth.synth_prompt_ids(cfg, batch=batch, prefix_len=7)
+            pix = synth.synth_pixels(cfg, batch=batch)
+            steps = 5
+            ref_t, ref_lg = O.generate_cached(sdb, cfg, ids, pix.to(torch.bfloat16), steps + 1, patched=True, return_logits=True)
+            _, truth = O.generate_cached(sd32, cfg, ids, pix, steps + 1, patched=True, return_logits=True, teacher=ref_t)
+            kv = eng.new_kv(batch)
+            kv.reserve(ids.shape[1] + steps + 1)
+            with torch.no_grad():
+                got = [eng.text_forward(ids.cuda(), eng.encode_images_dp(pix.cuda()), kv, logits="last")[:, -1].cpu()]
+            ds = eng.decode_state(batch)
+            ds.bind(kv, ref_t[:, 0].cuda(), position=ids.shape[1] + 1)
+            ds.want_full_logits = True
+            for t in range(steps):
+                ds.ids.copy_(ref_t[:, t].cuda())
+                ds.run_steps(kv, 1)
+                got.append(ds.logits.cpu().clone())
+            kv.release()
+            got = torch.stack(got, 1)
+            rms = lambda x: float(x.float().pow(2).mean().sqrt())
+            ref_noise, our_noise, delta = rms(ref_lg - truth), rms(got - truth), rms(got - ref_lg)
+            good = our_noise <= 1.5 * ref_noise + 1e-3 * rms(truth) and delta <= 2.5 * ref_noise + 1e-3 * rms(truth)
+            ok &= good
+            print(f"[rank {rank}] small bf16 batch {batch} tp={world}: ours-vs-fp32 {our_noise:.3g}, reference-bf16-vs-fp32 "
+                  f"{ref_noise:.3g}, ours-vs-reference {delta:.3g} -> {'OK' if good else 'FAIL'}", flush=True)
+    fab = eng.fabric if "eng" in dir() else None
+    if fab is not None:
+        torch.cuda.synchronize()
+        ok &= not fab.lost_peer()
+        print(f"[rank {rank}] peer-memory exchange used: {int(fab.epoch.item())} decode steps, lost-peer flag "
+              f"{int(fab.lost_peer())}", flush=True)
     else:
-        print(f"[rank {rank}] NCCL all-reduce path", flush=True)
+        print(f"[rank {rank}] NCCL collective path", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     passed = int(flag.item()) == 1
