@@ -66,6 +66,8 @@ class PagedKV:
     """Device state of one batch of sequences in the paged KV pool (the storage behind the
     reference's KVCache, modeling_gemma.py:10-36)."""
 
+    MIN_TABLE_PAGES = 256                    # table columns allocated up front (16 K tokens at 64 per page)
+
     def __init__(self, engine: "PaliGemmaEngine", batch: int):
         self.engine = engine
         self.batch = batch
@@ -76,16 +78,25 @@ class PagedKV:
         self.kv_len = torch.zeros(batch, dtype=torch.int32, device=engine.device)
 
     def reserve(self, total_len: int) -> None:
-        """Make sure every sequence owns pages for `total_len` entries."""
+        """Make sure every sequence owns pages for `total_len` entries.  The device page table is allocated once with
+        room for MIN_TABLE_PAGES pages per sequence and filled in place as pages are added, so its address and row
+        stride never change while a sequence grows: a decode graph captured over it stays valid."""
         eng = self.engine
         need = (total_len + eng.page_size - 1) // eng.page_size
-        if need <= len(self.pages[0]):
+        have = len(self.pages[0])
+        if need <= have:
             return
-        grow = max(need, min(2 * len(self.pages[0]), need + 8))
+        grow = max(need, min(2 * have, need + 8))
+        if self.page_table is None or grow > self.max_pages:
+            cap = max(self.MIN_TABLE_PAGES, 2 * grow)
+            table = torch.zeros((self.batch, cap), dtype=torch.int32, device=eng.device)
+            if self.page_table is not None and have:
+                table[:, :have].copy_(self.page_table[:, :have])
+            self.page_table, self.max_pages = table, cap
+        new = [eng._alloc_pages(grow - have) for _ in range(self.batch)]
         for b in range(self.batch):
-            self.pages[b].extend(eng._alloc_pages(grow - len(self.pages[b])))
-        self.max_pages = grow
-        self.page_table = torch.tensor(self.pages, dtype=torch.int32, device=eng.device)
+            self.pages[b].extend(new[b])
+        self.page_table[:, have:grow].copy_(torch.tensor(new, dtype=torch.int32))
 
     def release(self) -> None:
         if self.engine is not None:
