@@ -4,9 +4,13 @@ The reference serves one request at a time (`inference.py:34-85`: batch 1, one i
 single prompt, `processing_paligemma.py:80`).  Here requests of different prompt lengths share ONE captured decode
 step: a fixed number of slots, each slot a row of a static page table over the engine's paged KV pool.
 
-  * admission: the request is prefilled alone (vision tower + projector + L layers over its N prompt tokens, exactly
-    `generate()`'s first call) into pages of its own; the page list is then moved into a free slot's row, the slot's
-    KV length / next id / position are written on the device and the sequence joins the running batch;
+  * admission: queued requests with the SAME prompt length are prefilled TOGETHER, as many as there are free slots
+    (one vision-tower batch, one text_forward over (B, N) tokens: the weights stream once for all of them; rows of a
+    batch never mix, so every row equals its own batch-1 prefill) into pages of their own; each page list is then moved
+    into a free slot's row, the slot's KV length / next id / position are written on the device and the sequence
+    joins the running batch.  Prompts of different lengths are prefilled in separate calls: padding them into one
+    call would need a per-sequence attention mask, which the reference rules out (`modeling_gemma.py:559`, and its
+    attention is unmasked: padded positions would be attended);
   * every iteration replays the decode graph `chunk` times for all slots (idle slots compute on a parking page and
     are reset between chunks), reads the chunk's tokens back once, retires sequences that hit EOS or their token
     budget and frees their pages;
@@ -111,6 +115,7 @@ class ContinuousBatcher:
         self.finished: Dict[int, Request] = {}
         self._next_rid = 0
         self.steps_run = 0
+        self.prefill_calls = 0    # text_forward calls spent on admission (batched over equal prompt lengths)
 
     def submit(self, input_ids: torch.Tensor, pixel_values: Optional[torch.Tensor], max_new_tokens: int,
                eos_token_id: Optional[int] = None) -> int:
@@ -127,45 +132,71 @@ class ContinuousBatcher:
         self.queue.append(r)
         return r.rid
 
-    # ---- admission: prefill alone, then move the pages into a slot
+    # ---- admission: prefill (batched over equal prompt lengths), then move the pages into slots
     @torch.no_grad()
-    def _admit(self, slot: int, r: Request) -> None:
+    def _admit(self, slots: List[int], reqs: List[Request]) -> None:
+        """Prefill `reqs` (all of one prompt length, all with or all without an image) in ONE forward and seat them
+        in `slots`.  A request that is finished by its first token (EOS / budget 1) never takes a slot."""
         eng = self.eng
-        ids = r.input_ids.to(eng.device)
+        from .generate import _pick
+        B = len(reqs)
+        ids = torch.cat([r.input_ids.to(eng.device) for r in reqs], 0)
         N = ids.shape[1]
-        kv1 = eng.new_kv(1)
+        kvb = eng.new_kv(B)
         try:
-            kv1.reserve(N + 1)
-            feats = eng.encode_images(r.pixel_values.to(eng.device)) if r.pixel_values is not None else None
-            logits = eng.text_forward(ids, feats, kv1, logits="last")
-            from .generate import _pick
+            kvb.reserve(N + 1)
+            feats = None
+            if reqs[0].pixel_values is not None:
+                feats = eng.encode_images(torch.cat([r.pixel_values.to(eng.device) for r in reqs], 0))
+            logits = eng.text_forward(ids, feats, kvb, logits="last")
             # the first token's draw takes its Philox offset from the request id (never the same uniform twice)
-            first = _pick(eng, logits[:, -1, :].contiguous(), self.sample, step=((r.rid + 1) << 16) & 0x3fffffff)
-            pages, kv1.pages = kv1.pages[0], [[]]          # ownership moves to the slot
+            first = _pick(eng, logits[:, -1, :].contiguous(), self.sample, step=((reqs[0].rid + 1) << 16) & 0x3fffffff)
+            pages, kvb.pages = kvb.pages, [[] for _ in range(B)]      # ownership moves to the slots
         except Exception:
-            self.queue.appendleft(r)                       # admission failed (e.g. pool exhausted): nothing is lost
+            for r in reversed(reqs):
+                self.queue.appendleft(r)                               # admission failed (e.g. pool exhausted): nothing is lost
             raise
         finally:
-            kv1.release()
-        tok = int(first.item())
-        r.tokens.append(tok)
-        if (r.eos_token_id is not None and tok == r.eos_token_id) or r.max_new_tokens == 1:
-            eng._free_pages(pages)
-            r.done = True
-            self.finished[r.rid] = r
-            return
-        self.kv.assign(slot, pages, N)
-        self.ds.ids[slot:slot + 1].copy_(first)
-        self.ds.pos[slot:slot + 1].fill_(N + 1)            # after t tokens the next one is fed at position N + t (Q3)
-        self.running[slot] = r
+            kvb.release()
+        toks = first.tolist()
+        free = list(slots)
+        self.prefill_calls += 1
+        for b, r in enumerate(reqs):
+            tok = int(toks[b])
+            r.tokens.append(tok)
+            if (r.eos_token_id is not None and tok == r.eos_token_id) or r.max_new_tokens == 1:
+                eng._free_pages(pages[b])
+                r.done = True
+                self.finished[r.rid] = r
+                continue
+            slot = free.pop(0)
+            self.kv.assign(slot, pages[b], N)
+            self.ds.ids[slot:slot + 1].copy_(first[b:b + 1])
+            self.ds.pos[slot:slot + 1].fill_(N + 1)        # after t tokens the next one is fed at position N + t (Q3)
+            self.running[slot] = r
+
+    def _next_group(self, n_free: int) -> List[Request]:
+        """Up to n_free queued requests sharing the head request's prompt length and image-ness, in queue order."""
+        head = self.queue[0]
+        key = (head.input_ids.shape[1], head.pixel_values is None)
+        group, rest = [], deque()
+        while self.queue:
+            r = self.queue.popleft()
+            if len(group) < n_free and (r.input_ids.shape[1], r.pixel_values is None) == key:
+                group.append(r)
+            else:
+                rest.append(r)
+        self.queue = rest
+        return group
 
     @torch.no_grad()
     def step(self) -> None:
         """One scheduler iteration: admit into free slots, run one chunk of decode steps, collect, retire."""
-        for slot in range(self.slots):
-            if slot not in self.running and self.queue:
-                while self.queue and slot not in self.running:
-                    self._admit(slot, self.queue.popleft())
+        while self.queue:
+            free = [s for s in range(self.slots) if s not in self.running]
+            if not free:
+                break
+            self._admit(free, self._next_group(len(free)))
         if not self.running:
             return
         n = min(self.chunk, min(r.max_new_tokens - len(r.tokens) for r in self.running.values()))

@@ -84,3 +84,68 @@ def test_processor_with_a_real_hf_tokenizer(checkpoint_dir):
     ref = np.asarray(img.resize((size, size), resample=Image.Resampling.BICUBIC)).astype(np.float32) / 255.0
     ref = ((ref - 0.5) / 0.5).transpose(2, 0, 1)
     np.testing.assert_allclose(px[0].numpy(), ref, rtol=0, atol=1e-6)
+
+
+def write_sentencepiece_tokenizer(path, vocab_size=200):
+    """A REAL SentencePiece model (trained here on a synthetic corpus: no network) stored the way the hub stores
+    Gemma's: tokenizer.model + tokenizer_config.json; `AutoTokenizer.from_pretrained` (reference utils.py:8) loads it."""
+    import random
+    import sentencepiece as spm
+    words = ("caption en describe the chart revenue grew by ten percent in q3 what is shown table figure axis value "
+             "total net income margin year over quarter").split()
+    rng = random.Random(0)
+    corpus = os.path.join(path, "corpus.txt")
+    with open(corpus, "w") as f:
+        for _ in range(2000):
+            f.write(" ".join(rng.choices(words, k=8)) + "\n")
+    spm.SentencePieceTrainer.train(input=corpus, model_prefix=os.path.join(path, "tokenizer"), vocab_size=vocab_size,
+                                   model_type="bpe", pad_id=0, eos_id=1, bos_id=2, unk_id=3, pad_piece="<pad>",
+                                   eos_piece="<eos>", bos_piece="<bos>", unk_piece="<unk>", user_defined_symbols=["\n"],
+                                   minloglevel=2)
+    os.remove(corpus)
+    os.remove(os.path.join(path, "tokenizer.vocab"))
+    with open(os.path.join(path, "tokenizer_config.json"), "w") as f:
+        json.dump({"tokenizer_class": "GemmaTokenizer", "bos_token": "<bos>", "eos_token": "<eos>", "pad_token": "<pad>",
+                   "unk_token": "<unk>"}, f)
+
+
+def test_processor_with_a_sentencepiece_tokenizer(tmp_path):
+    """The processor driven by a SentencePiece-backed Gemma tokenizer: `<image>` is appended right after the base
+    vocabulary (processing_paligemma.py:63-66), the prompt is image tokens + <bos> + text + newline (:10-11)."""
+    from PIL import Image
+    from transformers import AutoTokenizer
+    d = str(tmp_path)
+    write_sentencepiece_tokenizer(d)
+    tok = AutoTokenizer.from_pretrained(d, padding_side="right")
+    assert type(tok).__name__.startswith("GemmaTokenizer")
+    n_before = len(tok)
+    proc = PP.PaliGemmaProcessor(tok, 16, 56)
+    assert proc.image_token_id == n_before
+    img = Image.fromarray(np.zeros((40, 52, 3), dtype=np.uint8), "RGB")
+    out = proc(text=["caption en"], images=[img])
+    ids = out["input_ids"][0].tolist()
+    assert ids[:16] == [n_before] * 16 and ids[16] == tok.bos_token_id
+    text_ids = ids[17:]
+    assert tok.decode(text_ids, skip_special_tokens=True).strip() == "caption en"
+    assert tok.decode(text_ids).endswith("\n")                    # the newline the processor appends survives the round trip
+
+
+def test_load_hf_model_refuses_an_incomplete_checkpoint(checkpoint_dir, tmp_path):
+    """A shard set that misses parameters must not leave uninitialised weights behind silently."""
+    import shutil
+    from safetensors.torch import load_file, save_file
+    d, cfg, sd, _ = checkpoint_dir
+    bad = str(tmp_path / "bad")
+    shutil.copytree(d, bad)
+    shard = os.path.join(bad, "model-00002-of-00002.safetensors")
+    part = load_file(shard)
+    dropped = sorted(part)[0]
+    del part[dropped]
+    save_file(part, shard)
+    with pytest.raises(RuntimeError, match="never loaded"):
+        U.load_hf_model(bad, device="cpu", dtype=torch.float32)
+    part["not.a.parameter"] = torch.zeros(3)
+    part[dropped] = sd[dropped]
+    save_file(part, shard)
+    with pytest.raises(RuntimeError, match="unexpected"):
+        U.load_hf_model(bad, device="cpu", dtype=torch.float32)

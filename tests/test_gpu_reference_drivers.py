@@ -147,3 +147,41 @@ def test_inference_driver_runs_unmodified(setup, capsys):
     I.main(model_path=ckpt, prompt="caption en", image_file_path=img_path, max_tokens_to_generate=4, do_sample=False)
     out = capsys.readouterr().out
     assert "Device in use:  cuda" in out and "caption en" in out
+
+
+def test_sentencepiece_checkpoint_decodes_on_the_gpu(setup, tmp_path):
+    """Checkpoint path end to end with a REAL SentencePiece tokenizer (trained offline on a synthetic corpus): config.json
+    + safetensors shards + tokenizer.model -> utils.load_hf_model -> PaliGemmaProcessor -> the reference's own
+    test_inference loop on the B200 engine -> text.  Tokens against the CPU oracle."""
+    from PIL import Image
+    from safetensors.torch import save_file
+    from test_checkpoint_cpu import write_sentencepiece_tokenizer
+    import inference as I
+    import utils as U
+    d = str(tmp_path)
+    write_sentencepiece_tokenizer(d)
+    from transformers import AutoTokenizer
+    n_tok = len(AutoTokenizer.from_pretrained(d))
+    cfg = json.loads(json.dumps(synth.TINY))
+    cfg["image_token_index"] = n_tok                               # where the processor will put <image>
+    cfg["vocab_size"] = cfg["text_config"]["vocab_size"] = n_tok + 1 + 1024 + 128 + (n_tok + 1) % 2
+    with open(os.path.join(d, "config.json"), "w") as f:
+        json.dump(cfg, f)
+    sd = {k: v.contiguous() for k, v in synth.synth_state_dict(cfg, tie=False).items()}
+    save_file(sd, os.path.join(d, "model.safetensors"))
+    img_path = os.path.join(d, "chart.png")
+    Image.fromarray(np.random.default_rng(5).integers(0, 256, size=(70, 90, 3), dtype=np.uint8), "RGB").save(img_path)
+    model, tokenizer = U.load_hf_model(d, "cuda", dtype=torch.float32)
+    model = model.to("cuda").eval()
+    v = model.config.vision_config
+    processor = PP.PaliGemmaProcessor(tokenizer, v.num_image_tokens, v.image_size)
+    inputs = processor(text=["describe the chart"], images=[Image.open(img_path)])
+    assert int((inputs["input_ids"] == n_tok).sum()) == v.num_image_tokens
+    n = 6
+    with torch.no_grad():
+        text = I.test_inference(model, processor, "cuda", "describe the chart", img_path, n, 0.8, 0.9, False)
+    sd["language_model.lm_head.weight"] = sd["language_model.model.embed_tokens.weight"]
+    want = O.generate_cached(sd, cfg, inputs["input_ids"], inputs["pixel_values"], n, patched=False)[0].tolist()
+    if tokenizer.eos_token_id in want:
+        want = want[:want.index(tokenizer.eos_token_id) + 1]
+    assert text == "describe the chart" + tokenizer.decode(torch.tensor(want), skip_special_tokens=True)

@@ -77,3 +77,26 @@ def test_continuous_batching_on_the_tensor_core_step_bf16():
         assert done[rid].tokens[0] == first[0]
         assert all(0 <= t < cfg["vocab_size"] for t in done[rid].tokens)
     cb.close()
+
+
+def test_batched_prefill_of_equal_length_prompts_fp32():
+    """Requests with the same prompt length are prefilled together (one vision batch + one text_forward per group of free
+    slots): tokens must still equal the CPU oracle's per-request greedy loop, and fewer prefill calls are spent."""
+    model, cfg = _model("tiny", torch.float32)
+    eng = model._engine_ready()
+    sd = synth.synth_state_dict(cfg)
+    reqs = []
+    for i, budget in enumerate((7, 4, 9, 5, 6, 3, 8)):
+        ids = synth.synth_prompt_ids(cfg, batch=1, prefix_len=8 if i != 3 else 11, seed=300 + i)
+        pix = synth.synth_pixels(cfg, batch=1, seed=400 + i)
+        reqs.append((ids, pix, budget))
+    want = [O.generate_cached(sd, cfg, ids, pix, budget, patched=True)[0].tolist() for ids, pix, budget in reqs]
+    free_before = len(eng._free)
+    cb = ContinuousBatcher(eng, slots=3, max_tokens=256, chunk=4)
+    rids = [cb.submit(ids, pix, budget) for ids, pix, budget in reqs]
+    done = cb.run()
+    for rid, w in zip(rids, want):
+        assert done[rid].tokens == w, (rid, done[rid].tokens, w)
+    assert cb.prefill_calls < len(reqs)                       # the first admission alone seats three requests in one call
+    cb.close()
+    assert len(eng._free) == free_before

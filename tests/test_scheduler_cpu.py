@@ -51,6 +51,7 @@ class StubEngine:
         self.slot_owner = {}
         self._ds = {}
         self.prefills = []
+        self.prefill_batches = []
 
     def _alloc_pages(self, n):
         assert n <= len(self._free), "pool exhausted"
@@ -72,13 +73,27 @@ class StubEngine:
         pass
 
     def text_forward(self, ids, feats, kv, logits="last"):
-        N = ids.shape[1]
+        B, N = ids.shape
         kv.reserve(N)
         kv.length = N
-        self.prefills.append(int(ids.sum()))
-        out = torch.full((1, 1, 64), -1.0)
-        out[0, 0, _stream(int(ids.sum()), 0)] = 1.0
+        out = torch.full((B, 1, 64), -1.0)
+        for b in range(B):
+            self.prefills.append(int(ids[b].sum()))
+            out[b, 0, _stream(int(ids[b].sum()), 0)] = 1.0
+        self.prefill_batches.append(B)
         return out
+
+
+def _track_owners(cb, eng):
+    """The stub model needs to know which request sits in which slot: record it when the scheduler seats a request."""
+    orig_admit = cb._admit
+    def admit(slots, reqs):
+        before = dict(cb.running)
+        orig_admit(slots, reqs)
+        for slot, r in cb.running.items():
+            if before.get(slot) is not r:
+                eng.slot_owner[slot] = (int(r.input_ids.sum()), r.input_ids.shape[1])
+    cb._admit = admit
 
 
 def _patch_pick(monkeypatch):
@@ -93,12 +108,7 @@ def test_scheduler_host_logic(monkeypatch):
     prompts = [torch.arange(1, 1 + n, dtype=torch.int64)[None] for n in (5, 9, 3, 6, 7)]
     budgets = [7, 2, 1, 9, 4]
 
-    # the stub needs to know which request sits in which slot: record it at assignment
-    orig_assign = cb.kv.assign
-    def assign(slot, pages, length):
-        eng.slot_owner[slot] = (eng.prefills[-1], length)
-        orig_assign(slot, pages, length)
-    cb.kv.assign = assign
+    _track_owners(cb, eng)
 
     rids = [cb.submit(p, None, b) for p, b in zip(prompts, budgets)]
     done = cb.run()
@@ -118,11 +128,7 @@ def test_scheduler_eos_and_capacity(monkeypatch):
     _patch_pick(monkeypatch)
     eng = StubEngine()
     cb = S.ContinuousBatcher(eng, slots=1, max_tokens=16, chunk=4)
-    orig_assign = cb.kv.assign
-    def assign(slot, pages, length):
-        eng.slot_owner[slot] = (eng.prefills[-1], length)
-        orig_assign(slot, pages, length)
-    cb.kv.assign = assign
+    _track_owners(cb, eng)
     p = torch.arange(1, 6, dtype=torch.int64)[None]
     stream = [_stream(int(p.sum()), t) for t in range(8)]
     eos = stream[4]
@@ -133,7 +139,6 @@ def test_scheduler_eos_and_capacity(monkeypatch):
     assert sorted(eng._free) == list(range(64))
     # a sequence that outgrows its slot is refused loudly
     cb = S.ContinuousBatcher(eng, slots=1, max_tokens=8, chunk=4)
-    cb.kv.assign = lambda slot, pages, length, f=cb.kv.assign: (eng.slot_owner.__setitem__(slot, (eng.prefills[-1], length)), f(slot, pages, length))[1]
     try:
         cb.submit(torch.arange(1, 7, dtype=torch.int64)[None], None, 10)     # 6 + 10 > 8: refused at submit()
         raise AssertionError("expected a capacity error")
@@ -148,11 +153,7 @@ def test_scheduler_history_ring_wraps(monkeypatch):
     _patch_pick(monkeypatch)
     eng = StubEngine(pages=256)
     cb = S.ContinuousBatcher(eng, slots=2, max_tokens=256, chunk=5)
-    orig_assign = cb.kv.assign
-    def assign(slot, pages, length):
-        eng.slot_owner[slot] = (eng.prefills[-1], length)
-        orig_assign(slot, pages, length)
-    cb.kv.assign = assign
+    _track_owners(cb, eng)
     prompts = [torch.arange(1, 1 + n, dtype=torch.int64)[None] for n in (4, 6, 5)]
     budgets = [150, 90, 70]
     rids = [cb.submit(p, None, b) for p, b in zip(prompts, budgets)]
@@ -160,5 +161,27 @@ def test_scheduler_history_ring_wraps(monkeypatch):
     for rid, p, b in zip(rids, prompts, budgets):
         assert done[rid].tokens == [_stream(int(p.sum()), t) for t in range(b)]
     assert int(cb.ds.step.item()) > cb.ds.max_hist                # wrapped at least once, never reset
+    cb.close()
+    assert sorted(eng._free) == list(range(256))
+
+
+
+def test_scheduler_batches_prefills_of_equal_length(monkeypatch):
+    """Queued requests with the same prompt length are admitted by ONE prefill call, as many as there are free slots;
+    different lengths go in separate calls; every request still gets exactly its own token stream."""
+    _patch_pick(monkeypatch)
+    eng = StubEngine(pages=256)
+    cb = S.ContinuousBatcher(eng, slots=4, max_tokens=64, chunk=4)
+    _track_owners(cb, eng)
+    lens = [6, 6, 6, 9, 6, 6, 9, 6]
+    prompts = [(torch.arange(1, 1 + n, dtype=torch.int64) * (i + 1) % 97 + 1)[None] for i, n in enumerate(lens)]
+    budgets = [5, 9, 3, 7, 4, 6, 2, 8]
+    rids = [cb.submit(p, None, b) for p, b in zip(prompts, budgets)]
+    done = cb.run()
+    for rid, p, b in zip(rids, prompts, budgets):
+        assert done[rid].tokens == [_stream(int(p.sum()), t) for t in range(b)], rid
+    assert eng.prefill_batches[0] == 4                       # the four free slots took the first four length-6 prompts at once
+    assert sum(eng.prefill_batches) == len(prompts) and len(eng.prefill_batches) < len(prompts)
+    assert cb.prefill_calls == len(eng.prefill_batches)
     cb.close()
     assert sorted(eng._free) == list(range(256))
