@@ -97,11 +97,18 @@ int pg_im2col(void* out, const void* pixels, int B, int C, int H, int W, int p, 
  * m % res_mod when res_mod > 0 (position-embedding broadcast over the batch).  out_f32 != 0
  * stores fp32 (lm_head `.float()`, modeling_gemma.py:417-418).  impl: 0 = auto, 1 = SIMT
  * (any dtype), 2 = tcgen05/TMA (bf16/f16 only; picks the CTA-pair, single-CTA, skinny or split-K kernel by shape),
- * 3 = the experimental swap-AB kernel for 128 < M <= 512.  Replaces every nn.Linear / matmul call site
+ * 3 = the CTA-pair swap-AB kernel for 129..512 rows (weights as the M operand, split-K through pg_set_workspace;
+ * auto takes it for the projections where it measured faster).  Replaces every nn.Linear / matmul call site
  * of SURVEY.md §2.3 on the prefill and vision paths. */
 int pg_gemm(void* C, const void* A, const void* W, const void* bias, const void* R,
             int M, int N, int K, int lda, int ldw, int ldc, int ldr, int res_mod,
             int epilogue, int out_f32, int impl, int dtype, void* stream);
+
+/* Scratch memory for GEMMs that split K over CTA pairs (prompt-sized row counts: csrc/gemm_tcgen05_swap.cu): a
+ * caller-owned device buffer the library may overwrite during any pg_gemm call on this device (fp32 partials
+ * [splits][M][N]); without one (or with one that is too small for a problem) pg_gemm takes its other kernels.
+ * The library never allocates. */
+int pg_set_workspace(void* ptr, long long bytes);
 
 /* RoPE on q and k + append of K,V to the paged cache (modeling_gemma.py:155-199, 23-36).
  * qkv: [B*q_len, (nq+2*nkv)*hd] from the fused projection; q_out: [B*q_len, nq*hd].

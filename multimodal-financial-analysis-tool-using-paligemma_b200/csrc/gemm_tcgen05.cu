@@ -279,13 +279,12 @@ bool gemm_tc_supported(int M, int N, int K, int lda, int ldw, int ldc, int epi, 
   return tc::encode_fn() != nullptr;
 }
 
+bool gemm_tc_swap_wanted(int M, int N, int K, int epi, int out_f32, int res_mod);
+int gemm_tc_swap(void* C, const void* A, const void* W, const void* R, int M, int N, int K, int lda, int ldw, int ldc,
+                 int ldr, int epi, int dtype, cudaStream_t st);
 bool gemm_tc_skinny_wanted(int M, int N, int K, int epi);
 int gemm_tc_skinny(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
                    int ldw, int ldc, int ldr, int epi, int out_f32, int dtype, cudaStream_t st);
-bool gemm_tc_wide_wanted(int M, int N, int K, int epi);
-bool gemm_tc_wide_supported(int M, int N, int K, int epi);
-int gemm_tc_wide(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
-                 int ldw, int ldc, int ldr, int epi, int out_f32, int dtype, cudaStream_t st);
 bool gemm_tc_2cta_wanted(int M, int N, int K, int epi);
 int gemm_tc_2cta(void* C, const void* A, const void* W, const void* bias, const void* R, int M, int N, int K, int lda,
                  int ldw, int ldc, int ldr, int res_mod, int epi, int out_f32, int dtype, cudaStream_t st);
@@ -301,10 +300,10 @@ int gemm_tc(void* C, const void* A, const void* W, const void* bias, const void*
   PG_REQUIRE(!R || (((uintptr_t)R % 16) == 0 && ldr % 8 == 0), "gemm_tc: residual must be 16-byte aligned rows");
   PG_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_tc: bias must be 16-byte aligned");
   const bool bf = dtype == PG_BF16;
+  if (gemm_tc_swap_wanted(M, N, K, epi, out_f32, res_mod))  // a prompt's worth of rows: CTA pairs, weights as the M operand
+    return gemm_tc_swap(C, A, W, R, M, N, K, lda, ldw, ldc, ldr, epi, dtype, st);
   if (res_mod == 0 && gemm_tc_skinny_wanted(M, N, K, epi))  // a few dozen token rows: stream the weights (swap-AB)
     return gemm_tc_skinny(C, A, W, bias, R, M, N, K, lda, ldw, ldc, ldr, epi, out_f32, dtype, st);
-  if (res_mod == 0 && gemm_tc_wide_wanted(M, N, K, epi))  // a prompt's worth of rows: swap-AB with every token in one accumulator
-    return gemm_tc_wide(C, A, W, bias, R, M, N, K, lda, ldw, ldc, ldr, epi, out_f32, dtype, st);
   {
     int sk_bn = 0;
     const int s = gemm_tc_splitk_factor(M, N, K, epi, &sk_bn);  // few tiles, long K: a cluster shares each tile

@@ -38,6 +38,7 @@ SIGNATURES = {
     "pg_resample_u8": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "pg_u8_to_chw": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "pg_gemm": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "pg_set_workspace": [_vp, _ll],
     "pg_rope_append": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "pg_attention": [_vp, _i, _vp, _i, _vp, _vp, _i, _ll, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
                      _f, _i, _i, _vp],

@@ -26,6 +26,9 @@ from ._cabi import exref, ptr
 from .dist import TP, check_divisible, combine_argmax_keys, shard_batch, shard_rows, shard_text_layer
 
 
+_WORKSPACES: Dict[tuple, torch.Tensor] = {}   # per device, kept for the life of the process (pg_set_workspace)
+
+
 def _get(obj, name, default=None):
     if isinstance(obj, Mapping):
         return obj.get(name, default)
@@ -180,6 +183,14 @@ class PaliGemmaEngine:
         self._err_np = self.err_flag.numpy()
         self.max_splits = 32
         self._decode_states: Dict[tuple, "DecodeState"] = {}
+        # scratch for the split-K prompt GEMMs (fp32 partials; 512 tokens x 2F features is the largest user)
+        if self.dtype != torch.float32:
+            key = (self.device.index, )
+            if key not in _WORKSPACES:
+                _WORKSPACES[key] = torch.empty(int(os.environ.get("PG_WORKSPACE_MB", "80")) << 20, dtype=torch.uint8,
+                                               device=self.device)
+            ws = _WORKSPACES[key]
+            cabi.check(cabi.lib().pg_set_workspace(ptr(ws), ws.numel()), "set_workspace")
         # tensor parallel: the peer-memory exchange the decode kernels use instead of collectives (dist.Fabric)
         self.fabric = self.tp.make_fabric(d.D, self.device)
         if self.fabric is not None and 2 * d.L + 2 > 4096:

@@ -490,40 +490,41 @@ def test_gemm_tcgen05_skinny_swap_ab(dtype, M, N, K, epi, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("M", [130, 260, 272, 273, 400, 512])
+@pytest.mark.parametrize("M", [129, 144, 260, 272, 300, 512])
 @pytest.mark.parametrize("N,K,epi", [(2560, 2048, "none"), (2048, 2048, "res"), (2048, 16384, "res"), (16384, 2048, "geglu"),
-                                     (8064, 2048, "f32"), (4304, 1152, "bias_gelu"), (1152, 4304, "bias_res"), (3840, 1152, "bias")])
-def test_gemm_tcgen05_wide_swap_ab(dtype, M, N, K, epi):
-    """Prompt-sized row counts (128 < M <= 512: the 260-token prefill, the cache-off recompute, the batch-1 vision
-    tower): swap-AB with every token in one TMEM accumulator (272 or 512 columns), persistent over weight tiles or
-    K-split across a cluster with the all-to-all DSMEM reduction, GeGLU with the 64+64 gate/up tile.  Experimental
-    path (impl=3): parity-green but measured slower than the row-major kernels, so not the default."""
-    if dtype == torch.float16 and M not in (260, 400):
+                                     (768, 2048, "none"), (1000, 1088, "res"), (2048, 4096, "geglu")])
+def test_gemm_tcgen05_prompt_rows_swapped_pairs(dtype, M, N, K, epi):
+    """Prompt-sized row counts (129..512: the 260-token prefill, the cache-off recompute up to 512 tokens) take the
+    CTA-pair kernel with the WEIGHTS as the M = 256 operand and all tokens in one or two accumulators, split along K
+    over the pairs, plus the reduce / epilogue pass (csrc/gemm_tcgen05_swap.cu).  Shapes: the Gemma projections at
+    tp 1 / tp 8 (768-row q/k/v shard) and ragged N / K tails.  Against torch in the same dtype."""
+    if dtype == torch.float16 and M not in (260, 512):
         pytest.skip("fp16 on two row counts only")
+    ws = torch.empty(80 << 20, dtype=torch.uint8, device="cuda")
+    cabi.check(cabi.lib().pg_set_workspace(ws.data_ptr(), ws.numel()))
     a = gen(M, K, dtype=dtype)
     s = 1.0 / math.sqrt(K)
     w, w2 = gen(N, K, seed=1, scale=s, dtype=dtype), gen(N, K, seed=2, scale=s, dtype=dtype)
-    bias, res = gen(N, seed=3, scale=0.1, dtype=dtype), gen(M, N, seed=4, dtype=dtype)
-    code = dict(none=cabi.EPI_NONE, res=cabi.EPI_RES, geglu=cabi.EPI_GEGLU, f32=cabi.EPI_NONE, bias_gelu=cabi.EPI_BIAS_GELU,
-                bias_res=cabi.EPI_BIAS_RES, bias=cabi.EPI_BIAS)[epi]
+    res = gen(M, N, seed=4, dtype=dtype)
+    code = dict(none=cabi.EPI_NONE, res=cabi.EPI_RES, geglu=cabi.EPI_GEGLU)[epi]
     if epi == "none":
         want = F.linear(a, w)
-    elif epi == "bias":
-        want = F.linear(a, w, bias)
     elif epi == "res":
         want = F.linear(a, w) + res
-    elif epi == "geglu":
-        want = F.gelu(F.linear(a, w), approximate="tanh") * F.linear(a, w2)
-    elif epi == "bias_gelu":
-        want = F.gelu(F.linear(a, w, bias), approximate="tanh")
-    elif epi == "bias_res":
-        want = F.linear(a, w, bias) + res
     else:
-        want = F.linear(a, w).float()
+        want = F.gelu(F.linear(a, w), approximate="tanh") * F.linear(a, w2)
     wd = dev(torch.cat([w, w2], 0)) if epi == "geglu" else dev(w)
-    ad, bd, rd = dev(a), dev(bias), dev(res)
-    out = torch.full((M, N), float("nan"), dtype=torch.float32 if epi == "f32" else dtype, device="cuda")
-    cabi.check(cabi.lib().pg_gemm(out.data_ptr(), ad.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), M, N, K, K, K,
-                                  N, N, 0, code, 1 if epi == "f32" else 0, 3, cabi.DTYPE_CODE[dtype], st()))
+    ad, rd = dev(a), dev(res)
+    out = torch.full((M, N), float("nan"), dtype=dtype, device="cuda")
+    before = cabi.launch_count()
+    cabi.check(cabi.lib().pg_gemm(out.data_ptr(), ad.data_ptr(), wd.data_ptr(), None, rd.data_ptr(), M, N, K, K, K, N, N, 0,
+                                  code, 0, 3, cabi.DTYPE_CODE[dtype], st()))
     torch.cuda.synchronize()
+    assert cabi.launch_count() - before == 2                       # the pair GEMM + its reduce / epilogue pass
     close(out, want, dtype)
+    # the same problem through the row-major tcgen05 kernels (PG_GEMM_SWAP off is an env switch read once, so compare
+    # with the SIMT path instead: same rounding points, different accumulation order)
+    ref = torch.empty_like(out)
+    cabi.check(cabi.lib().pg_gemm(ref.data_ptr(), ad.data_ptr(), wd.data_ptr(), None, rd.data_ptr(), M, N, K, K, K, N, N, 0,
+                                  code, 0, 1, cabi.DTYPE_CODE[dtype], st()))
+    close(out, ref.cpu(), dtype)
