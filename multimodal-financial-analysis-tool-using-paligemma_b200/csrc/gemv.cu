@@ -98,9 +98,18 @@ struct RowStreamer {
   template <typename RowsFn, typename DoneFn>
   __device__ __forceinline__ void run(long long n_units, long long stride, const float* xs, const T* xg, int K,
                                       int k_begin, int k_end, RowsFn rows, DoneFn done) {
+    run(n_units, stride, xs, xg, K, k_begin, k_end, rows, done, [](long long) {});
+  }
+
+  // pre(u) runs before unit u's rows are consumed: epilogue inputs that do not depend on the dot products (addresses,
+  // angles) are fetched / computed while the weight loads are in flight instead of after the reduction
+  template <typename RowsFn, typename DoneFn, typename PreFn>
+  __device__ __forceinline__ void run(long long n_units, long long stride, const float* xs, const T* xg, int K,
+                                      int k_begin, int k_end, RowsFn rows, DoneFn done, PreFn pre) {
     const int lane_off = (int)(threadIdx.x & 31) * V;
     bool primed = true;  // the first stage of the first unit was loaded by prime()
     while (u < n_units) {
+      pre(u);
       float acc[R][NB];
 #pragma unroll
       for (int r = 0; r < R; ++r)
@@ -257,7 +266,18 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
   RowStreamer<T, NB, 2, QKV_U, true> rs;
   rs.prime(warp, units, 0, D, rows);
   pdl_wait();
+  // lane b < NB owns batch row b in the epilogue: its cache slot and position do not depend on the projections, so
+  // they are fetched here (the loads overlap the norm prologue) and the RoPE angle of a unit is computed in pre()
+  size_t kv_row = 0;
+  int pos = 0;
+  if (lane < NB) {
+    const int slot = kv_len[lane];
+    const int page = page_table[(size_t)lane * pt_stride + slot / page_size];
+    kv_row = ((size_t)page * page_size + (slot % page_size)) * (size_t)(nkv * hd);
+    pos = min(max(positions[lane], 0), max_pos - 1);
+  }
   prologue_rows<T, NB, TPX>(xs, x, x_out, norm_w, D, eps, ex);
+  float rc = 1.f, rsn = 0.f;
   rs.run(units, nwarps, xs, nullptr, D, 0, D, rows, [&](long long u, float (&acc)[2][NB]) {
     if (lane < NB) {
       const int h = (int)u / half, j = (int)u % half;
@@ -266,14 +286,8 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
       for (int b = 0; b < NB; ++b) if (b == lane) { a1 = acc[0][b]; a2 = acc[1][b]; }
       const int b = lane;
       const float x1 = rnd<T>(a1), x2 = rnd<T>(a2);
-      const int slot = kv_len[b];
-      const int page = page_table[(size_t)b * pt_stride + slot / page_size];
-      const size_t kv_row = ((size_t)page * page_size + (slot % page_size)) * (size_t)(nkv * hd);
       if (h < nq + nkv) {
-        int pos = positions[b];
-        pos = min(max(pos, 0), max_pos - 1);
-        const float ang = (float)pos * inv_freq[j];
-        const float c = rnd<T>(cosf(ang)), s = rnd<T>(sinf(ang));
+        const float c = rc, s = rsn;
         const float o1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(-x2 * s));
         const float o2 = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
         if (h < nq) {
@@ -290,6 +304,12 @@ decode_qkv_kernel(T* __restrict__ q_out, const T* __restrict__ x, const T* __res
         vo[j] = from_f<T>(x1);
         vo[j + half] = from_f<T>(x2);
       }
+    }
+  }, [&](long long u) {
+    if (lane < NB && (int)u / half < nq + nkv) {
+      const float ang = (float)pos * inv_freq[(int)u % half];
+      rc = rnd<T>(cosf(ang));
+      rsn = rnd<T>(sinf(ang));
     }
   });
 }

@@ -44,8 +44,14 @@ def main():
     B = int(os.environ.get("SWEEP_B", "1"))
     T = int(os.environ.get("SWEEP_T", "300"))
     cfg = synth.CONFIGS["paligemma-3b-pt-224"]
-    eng = PaliGemmaEngine(cfg, gpu_weights(cfg, torch.bfloat16))
+    tp_size = int(os.environ.get("SWEEP_TP", "1"))      # > 1: rank 0's SHARD shapes, kernels timed without the exchange
+    tp = None
+    if tp_size > 1:
+        from pg_b200.dist import TP, Fabric
+        tp = TP(0, tp_size, fabric=Fabric.emulated(tp_size, cfg["text_config"]["hidden_size"], "cuda")[0], emulated=True)
+    eng = PaliGemmaEngine(cfg, gpu_weights(cfg, torch.bfloat16), tp=tp)
     d, L, st, dt = eng.dims, cabi.lib(), cabi.stream(), eng.dt
+    nq, F_l, V_l = eng.nq_l, eng.F_l, eng.V_l
     kv = eng.new_kv(B)
     kv.reserve(T + 600)
     kv.length = T
@@ -74,39 +80,43 @@ def main():
         for li, w in enumerate(eng.t_layers):
             L.pg_decode_qkv(ds.q.data_ptr(), ds.x.data_ptr(), w["ln1"].data_ptr(), w["qkv"].data_ptr(), eng.inv_freq.data_ptr(),
                             ds.pos.data_ptr(), eng.k_pool[li].data_ptr(), eng.v_pool[li].data_ptr(), kv.page_table.data_ptr(),
-                            kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), B, d.D, d.nq, d.nkv, d.hd, d.eps, d.max_pos, None, None, dt, st)
-    rec("qkv", qkv, e * (d.nq + 2 * d.nkv) * d.hd * d.D)
+                            kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), B, d.D, nq, d.nkv, d.hd, d.eps, d.max_pos, None, None, dt, st)
+    rec("qkv", qkv, e * (nq + 2 * d.nkv) * d.hd * d.D)
 
     def attn():
         for li, w in enumerate(eng.t_layers):
             L.pg_decode_attention(ds.att.data_ptr(), ds.q.data_ptr(), eng.k_pool[li].data_ptr(), eng.v_pool[li].data_ptr(),
-                                  kv.page_table.data_ptr(), kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), 1, B, d.nq, d.nkv,
+                                  kv.page_table.data_ptr(), kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), 1, B, nq, d.nkv,
                                   d.hd, 16.0, None, None, 32, dt, st)
     rec("attention", attn, e * B * 2 * (T + 1) * d.nkv * d.hd)
 
     def oproj():
         for li, w in enumerate(eng.t_layers):
-            L.pg_gemv_res(ds.x2.data_ptr(), ds.att.data_ptr(), w["o"].data_ptr(), ds.x.data_ptr(), B, d.D, d.nq * d.hd, None, dt, st)
-    rec("o_proj", oproj, e * d.D * d.nq * d.hd)
+            L.pg_gemv_res(ds.x2.data_ptr(), ds.att.data_ptr(), w["o"].data_ptr(), ds.x.data_ptr(), B, d.D, nq * d.hd, None, dt, st)
+    rec("o_proj", oproj, e * d.D * nq * d.hd)
 
     def gateup():
         for li, w in enumerate(eng.t_layers):
-            L.pg_decode_gateup(ds.g.data_ptr(), ds.x2.data_ptr(), w["ln2"].data_ptr(), w["gu"].data_ptr(), B, d.D, d.F, d.eps, None, None, dt, st)
-    rec("gateup", gateup, e * 2 * d.F * d.D)
+            L.pg_decode_gateup(ds.g.data_ptr(), ds.x2.data_ptr(), w["ln2"].data_ptr(), w["gu"].data_ptr(), B, d.D, F_l, d.eps, None, None, dt, st)
+    rec("gateup", gateup, e * 2 * F_l * d.D)
 
     def down():
         for li, w in enumerate(eng.t_layers):
-            L.pg_gemv_res(ds.x.data_ptr(), ds.g.data_ptr(), w["down"].data_ptr(), ds.x2.data_ptr(), B, d.D, d.F, None, dt, st)
-    rec("down", down, e * d.F * d.D)
+            L.pg_gemv_res(ds.x.data_ptr(), ds.g.data_ptr(), w["down"].data_ptr(), ds.x2.data_ptr(), B, d.D, F_l, None, dt, st)
+    rec("down", down, e * F_l * d.D)
 
     def lmhead():
-        L.pg_decode_lmhead(ds.logits.data_ptr(), ds.x.data_ptr(), eng.final_norm.data_ptr(), eng.lm_head.data_ptr(), B, d.D, d.V,
+        L.pg_decode_lmhead(ds.local_logits.data_ptr(), ds.x.data_ptr(), eng.final_norm.data_ptr(), eng.lm_head.data_ptr(), B, d.D, V_l,
                            d.eps, ds.keys.data_ptr(), None, None, dt, st)
     med, mn = timeit(lmhead, 1)
-    res["lm_head"] = {"us": round(med, 2), "min_us": round(mn, 2), "GBps": round(e * d.V * d.D / med / 1e3, 1)}
+    res["lm_head"] = {"us": round(med, 2), "min_us": round(mn, 2), "GBps": round(e * V_l * d.D / med / 1e3, 1)}
 
     per_layer = sum(res[k]["us"] for k in ("qkv", "attention", "o_proj", "gateup", "down"))
     res["sum_isolated_us"] = round(nl * per_layer + res["lm_head"]["us"], 1)
+    if tp_size > 1:      # an emulated rank cannot run a step alone (its consumers would wait for the other ranks)
+        res["tp"] = tp_size
+        print(json.dumps(res))
+        return
     # whole step through the graph
     ds.run_steps(kv, 1)
     g = next(iter(ds.graphs.values()))
