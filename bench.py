@@ -495,21 +495,25 @@ def run_ours(args, rank, world, local):
         nxt = out["logits"][:, -1].argmax(-1, keepdim=True)
         host_ids.copy_(nxt)
         torch.cuda.synchronize()
+        e2e_steps = []
         for i in range(W + K):
             if i == W:
                 barrier(world)
                 t0 = time.perf_counter()
+            ts = time.perf_counter()
             cur = host_ids.to("cuda", non_blocking=True)                   # H2D: this step's input ids
             mask = torch.cat([mask, torch.ones((B, 1), dtype=mask.dtype, device="cuda")], -1)
             out = head_model(input_ids=cur, pixel_values=None, attention_mask=mask, kv_cache=kvc)
             nxt = out["logits"][:, -1].argmax(-1, keepdim=True)
             host_tok.copy_(nxt, non_blocking=False)                          # D2H: the step's result
             host_ids.copy_(host_tok)
+            if i >= W:
+                e2e_steps.append((time.perf_counter() - ts) * 1e3)
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(e2e_ms, world)
     e2e = {"value": streams * B * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * B,
-           "d2h_bytes_per_step": 8 * B, "ms_per_step": e2e_ms / K,
+           "d2h_bytes_per_step": 8 * B, "ms_per_step": e2e_ms / K, "ms_per_step_spread": spread(e2e_steps),
            "api": "PaliGemmaForConditionalGeneration.forward(input_ids, pixel_values, attention_mask, kv_cache) per token"}
     kvc._paged.release()
 

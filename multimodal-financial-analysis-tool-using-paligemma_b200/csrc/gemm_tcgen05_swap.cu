@@ -285,12 +285,15 @@ static void swap_plan(int M, int N, int K, tc::ParamsSw* p) {
 
 bool gemm_tc_swap_wanted(int M, int N, int K, int epi, int out_f32, int res_mod) {
   static const int enabled = env_int("PG_GEMM_SWAP", 1);
-  static const int min_m = env_int("PG_GEMM_SWAP_MIN_M", 129);
+  static const int min_m = env_int("PG_GEMM_SWAP_MIN_M", 4);
   if ((!enabled && !g_force_swap) || out_f32 || res_mod != 0 || M < min_m || M > 512) return false;
   if (epi != PG_EPI_NONE && epi != PG_EPI_RES && epi != PG_EPI_GEGLU) return false;
   // which projections take this kernel (measured per projection, profiles/README.md): bit 0 q/k/v (no epilogue),
   // bit 1 o_proj (residual, K < 8192), bit 2 down_proj (residual, K >= 8192), bit 3 gate/up (GeGLU)
-  static const int mask = env_int("PG_SWAP_MASK", 4);
+  // measured: prompt-sized rows (129..512) -- down_proj only (prefill 4.16 -> 3.45 ms; q/k/v, o_proj and gate/up are
+  // faster on the row-major kernels); batched-decode rows (4..128) -- o_proj and down_proj (batch 32: 1.93 -> 1.86 ms)
+  static const int mask_large = env_int("PG_SWAP_MASK", 4), mask_small = env_int("PG_SWAP_MASK_SMALL", 6);
+  const int mask = M > 128 ? mask_large : mask_small;
   const int kind = epi == PG_EPI_NONE ? 1 : (epi == PG_EPI_GEGLU ? 8 : (K >= 8192 ? 4 : 2));
   if (!(mask & kind) && !g_force_swap) return false;
   const int n_w = epi == PG_EPI_GEGLU ? 2 * N : N;   // weight rows

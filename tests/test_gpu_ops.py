@@ -490,11 +490,12 @@ def test_gemm_tcgen05_skinny_swap_ab(dtype, M, N, K, epi, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("M", [129, 144, 260, 272, 300, 512])
+@pytest.mark.parametrize("M", [8, 32, 100, 129, 144, 260, 272, 300, 512])
 @pytest.mark.parametrize("N,K,epi", [(2560, 2048, "none"), (2048, 2048, "res"), (2048, 16384, "res"), (16384, 2048, "geglu"),
                                      (768, 2048, "none"), (1000, 1088, "res"), (2048, 4096, "geglu")])
 def test_gemm_tcgen05_prompt_rows_swapped_pairs(dtype, M, N, K, epi):
-    """Prompt-sized row counts (129..512: the 260-token prefill, the cache-off recompute up to 512 tokens) take the
+    """Prompt-sized row counts (129..512: the 260-token prefill, the cache-off recompute up to 512 tokens; also the
+    batched-decode rows 4..128 for the residual projections) take the
     CTA-pair kernel with the WEIGHTS as the M = 256 operand and all tokens in one or two accumulators, split along K
     over the pairs, plus the reduce / epilogue pass (csrc/gemm_tcgen05_swap.cu).  Shapes: the Gemma projections at
     tp 1 / tp 8 (768-row q/k/v shard) and ragged N / K tails.  Against torch in the same dtype."""

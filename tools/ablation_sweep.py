@@ -119,8 +119,11 @@ def main():
     rank, world, local = bench.dist_setup()
     cfg = synth.CONFIGS["paligemma-3b-pt-224"]
     sd = bench.build_weights_gpu(cfg, torch.bfloat16)
-    eng = PaliGemmaEngine(cfg, sd)                                  # every rank's own copy (cache-off loop)
-    eng_tp = PaliGemmaEngine(cfg, sd, tp=TP(rank, world, None)) if world > 1 else eng
+    pool = dict(kv_pool_tokens=8192)                                # one sequence of <= 516 + 256 tokens at a time
+    eng = PaliGemmaEngine(cfg, sd, **pool)                          # every rank's own copy (cache-off loop)
+    eng_tp = PaliGemmaEngine(cfg, sd, tp=TP(rank, world, None), **pool) if world > 1 else eng
+    del sd                                                          # the engines hold (fused / sharded) copies of what they use
+    torch.cuda.empty_cache()
     ids, pix = synth.synth_prompt_ids(cfg).cuda(), synth.synth_pixels(cfg).cuda()
     weights_mb = eng_tp.weight_bytes_per_decode_step() / 2 ** 20
     out = {}
