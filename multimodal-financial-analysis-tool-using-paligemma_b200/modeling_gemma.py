@@ -324,12 +324,18 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         self._engine = None
         return res
 
+    def _fingerprint_modules(self):
+        ms = getattr(self, "_fp_modules", None)
+        if ms is None:      # module objects are stable (only their parameters' storage moves); look them up once
+            ms = self._fp_modules = (self.language_model.model.embed_tokens, self.language_model.lm_head,
+                                     self.language_model.model.layers[-1].mlp.down_proj,
+                                     self.vision_tower.vision_model.embeddings.patch_embedding,
+                                     self.multi_modal_projector.linear)
+        return ms
+
     def _fingerprint(self):
-        ts = (self.language_model.model.embed_tokens.weight, self.language_model.lm_head.weight,
-              self.language_model.model.layers[-1].mlp.down_proj.weight,
-              self.vision_tower.vision_model.embeddings.patch_embedding.weight,
-              self.multi_modal_projector.linear.weight)
-        return tuple((t.data_ptr(), t.dtype, str(t.device)) for t in ts)
+        # storage address + dtype + device of five parameters spread over the model: any .to() / load / re-tie moves them
+        return tuple((m.weight.data_ptr(), m.weight.dtype, m.weight.device) for m in self._fingerprint_modules())
 
     def _engine_ready(self) -> PaliGemmaEngine:
         if self._engine is None or self._fingerprint() != self._engine_key:

@@ -105,7 +105,12 @@ def exref(ex):
 
 
 def stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current stream on the current device (the private accessor is ~20x cheaper than building
+    a torch.cuda.Stream object per kernel launch; fall back to the public API if it ever goes away)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:
+        return torch.cuda.current_stream().cuda_stream
 
 
 def launch_count() -> int:
