@@ -50,7 +50,9 @@ class Fabric:
         self.keys_off = 2 * size * self.x_slot
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.err_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.err_host = torch.zeros(1, dtype=torch.int32)
+        if dev.type == "cuda":
+            self.err_host = self.err_host.pin_memory()      # device-mapped: the kernels' timeout flag is readable without a sync
         self._err_np = self.err_host.numpy()
         self._cache: Dict[tuple, Exchange] = {}
 
