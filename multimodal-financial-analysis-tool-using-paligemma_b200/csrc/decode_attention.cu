@@ -48,8 +48,12 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
   if (OPROJ) {
     const T* src = w_o + (size_t)rank * rows_per * k_o;
     const int n_vec = rows_per * k_o / V;
-    for (int i = threadIdx.x; i < n_vec; i += DC_WARPS * 32)
-      *reinterpret_cast<uint4*>(w_s + (size_t)i * V) = ldg_stream(src + (size_t)i * V);
+    // asynchronous copies (LDGSTS): all of them are in flight at once and nothing waits for them until the o_proj phase
+    for (int i = threadIdx.x; i < n_vec; i += DC_WARPS * 32) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(w_s + (size_t)i * V);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)i * V) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   pdl_wait();  // q and this step's K/V row come from the preceding qkv kernel
   const int T_len = kv_len[b] + kv_len_add;
@@ -310,7 +314,8 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
       out[(size_t)b * nq * hd + (size_t)(kvh * G + g) * hd + (e % hd)] = o;
     }
   }
-  cluster.sync();  // nobody leaves while a peer may still read its shared memory (and att_s is complete everywhere)
+  if (OPROJ) asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's part of the shard has landed
+  cluster.sync();  // nobody leaves while a peer may still read its shared memory (att_s and the shard are complete)
   if (OPROJ) {
     // o_proj partial of this rank for rows [rank * rows_per, +rows_per): one warp per row, lanes along K as gemv_res does
     const uint32_t seq = tp_seq(ex);
@@ -322,11 +327,9 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
 #pragma unroll
         for (int i = 0; i < V; ++i) acc = fmaf(wf[i], att_s[k + i], acc);
       }
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        const long long word = (long long)b * d_out + rank * rows_per + r;
-        for (int p = 0; p < ex.tp; ++p) tp_store_word(tp_slot(ex, p, seq, ex.rank), word, acc, seq);
-      }
+      acc = warp_sum(acc);          // every lane holds the sum: lane p stores it into rank p's buffer (one instruction per row)
+      if (lane < ex.tp)
+        tp_store_word(tp_slot(ex, lane, seq, ex.rank), (long long)b * d_out + rank * rows_per + r, acc, seq);
     }
   }
 }

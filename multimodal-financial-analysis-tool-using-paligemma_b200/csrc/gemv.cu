@@ -362,17 +362,33 @@ gemv_res_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restric
       }
       parity ^= 1;  // double-buffered: the next iteration's writes cannot race these reads
     }
-    if (ks == 0 && n < N && lane < NB) {
+    if constexpr (TPX) {
+      // every lane of the ks == 0 warp holds the row's sums: lane (b, p) stores batch row b into rank p's buffer, so
+      // the tp peer stores of a row are ONE instruction (lane 0 issuing them one after the other cost ~1.7 us at tp 8)
+      if (ks == 0 && n < N) {
+        const int tpn = ex.tp;
+        if (NB * tpn <= 32) {
+          if (lane < NB * tpn) {
+            const int bb = lane / tpn, p = lane % tpn;
+            float a = 0.f;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) if (b == bb) a = acc[0][b];
+            tp_store_word(tp_slot(ex, p, seq, ex.rank), (long long)bb * N + n, a, seq);
+          }
+        } else if (lane < NB) {
+          float a = 0.f;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) if (b == lane) a = acc[0][b];
+          for (int p = 0; p < tpn; ++p) tp_store_word(tp_slot(ex, p, seq, ex.rank), (long long)lane * N + n, a, seq);
+        }
+      }
+    } else if (ks == 0 && n < N && lane < NB) {
       float a = 0.f;
 #pragma unroll
       for (int b = 0; b < NB; ++b) if (b == lane) a = acc[0][b];
-      if constexpr (TPX) {
-        for (int p = 0; p < ex.tp; ++p) tp_store_word(tp_slot(ex, p, seq, ex.rank), (long long)lane * N + n, a, seq);
-      } else {
-        float v = rnd<T>(a);
-        if (R) v = rnd<T>(to_f<T>(R[(size_t)lane * N + n]) + v);
-        out[(size_t)lane * N + n] = from_f<T>(v);
-      }
+      float v = rnd<T>(a);
+      if (R) v = rnd<T>(to_f<T>(R[(size_t)lane * N + n]) + v);
+      out[(size_t)lane * N + n] = from_f<T>(v);
     }
   });
 }
