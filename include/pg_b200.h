@@ -176,16 +176,6 @@ int pg_decode_attention(void* out, const void* q, const void* k_pool, const void
                         float scale_div, float* ws, int* counters, int max_splits, int dtype,
                         void* stream);
 
-/* Tensor parallel with 1-2 local query heads (tp 4 / tp 8 of PaliGemma-3B): pg_decode_attention, the o_proj of this
- * rank's heads (w_o: its [d_out, nq*hd] column shard, modeling_gemma.py:291) and the producer side of the exchange in
- * ONE launch: every CTA of the 16-CTA cluster stages d_out/16 rows of the shard before the dependency wait, the
- * attention row is broadcast through distributed shared memory, and the fp32 partials go straight into every rank's
- * exchange buffer (words b*d_out + n), exactly what pg_gemv_res(ex) would have pushed.  One KV head, B <= 9. */
-int pg_decode_attention_oproj(const void* q, const void* k_pool, const void* v_pool, const int32_t* page_table,
-                              int pt_stride, int page_size, const int32_t* kv_len, int kv_len_add, int B, int nq,
-                              int hd, float scale_div, const void* w_o, int d_out, const pg_tp_exchange* ex,
-                              int dtype, void* stream);
-
 /* out[B,N] = (x[B,K] W[N,K]^T) + R  — o_proj / down_proj with the residual add
  * (modeling_gemma.py:291,327 and :134,336).  R may be NULL.  ex != NULL (tensor parallel: W holds this rank's K
  * columns): the unrounded fp32 partial x W^T goes to word b*N+n of this rank's slot in every rank's exchange buffer

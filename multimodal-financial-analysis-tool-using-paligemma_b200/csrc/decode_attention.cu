@@ -13,7 +13,6 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
-#include "tp_exchange.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -22,17 +21,13 @@ namespace pg {
 constexpr int DC_WARPS = 8;     // warps per CTA
 constexpr int DC_MAX_PT = 1024; // page-table entries staged in shared memory
 
-// OPROJ (tensor parallel, few local heads): the cluster goes on to multiply its attention row with this rank's o_proj
-// shard -- CTA r owns D_out / DC_NS output rows, staged in shared memory BEFORE the dependency wait (weights never
-// depend on activations) -- and stores the fp32 partials straight into every rank's exchange buffer (tp_exchange.cuh):
-// attention + o_proj + the "all-reduce" producer are one launch.  Needs nkv == 1 (all local heads in this cluster).
-template <typename T, int G, int NCH, int TB, int DC_NS, bool OPROJ>
+template <typename T, int G, int NCH, int TB, int DC_NS>
 __global__ void __launch_bounds__(DC_WARPS * 32, 1)
 decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, const T* __restrict__ k_pool,
                                 const T* __restrict__ v_pool, const int32_t* __restrict__ page_table,
                                 int pt_stride, int page_size, const int32_t* __restrict__ kv_len,
                                 int kv_len_add, int nq, int nkv, int hd, float scale_div, float scale_mul,
-                                Prefetch pf, const T* __restrict__ w_o, int d_out, TpEx ex) {
+                                Prefetch pf) {
   constexpr int V = Vec<T>::N;
   cg::cluster_group cluster = cg::this_cluster();
   pdl_launch_dependents();
@@ -40,25 +35,11 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y, kvh = blockIdx.z;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  extern __shared__ __align__(16) float sm[];
-  // fused o_proj: this CTA's rows of the shard, [rows_per][G * hd] in the model dtype, behind the attention scratch
-  const int k_o = G * hd, rows_per = OPROJ ? d_out / DC_NS : 0;
-  float* att_s = sm + ((((size_t)DC_WARPS * G * hd + 2 * DC_WARPS * G + (size_t)G * hd + 2 * G) + 3) & ~(size_t)3);   // [G * hd] full row, 16-byte aligned
-  T* w_s = reinterpret_cast<T*>(att_s + k_o);
-  if (OPROJ) {
-    const T* src = w_o + (size_t)rank * rows_per * k_o;
-    const int n_vec = rows_per * k_o / V;
-    // asynchronous copies (LDGSTS): all of them are in flight at once and nothing waits for them until the o_proj phase
-    for (int i = threadIdx.x; i < n_vec; i += DC_WARPS * 32) {
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(w_s + (size_t)i * V);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)i * V) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
   pdl_wait();  // q and this step's K/V row come from the preceding qkv kernel
   const int T_len = kv_len[b] + kv_len_add;
   const int row_elems = nkv * hd;
 
+  extern __shared__ __align__(16) float sm[];
   float* s_acc = sm;                                     // [DC_WARPS][G][hd]
   float* s_m = s_acc + (size_t)DC_WARPS * G * hd;        // [DC_WARPS][G]
   float* s_l = s_m + DC_WARPS * G;                       // [DC_WARPS][G]
@@ -305,52 +286,22 @@ decode_attention_cluster_kernel(T* __restrict__ out, const T* __restrict__ q, co
         a = fmaf(w, pa[r], a);
         L = fmaf(w, pl[r], L);
       }
-    const T o = from_f<T>(a / L);
-    if (OPROJ) {
-      const float of = to_f<T>(o);
-#pragma unroll
-      for (int r = 0; r < DC_NS; ++r) *cluster.map_shared_rank(att_s + e, r) = of;   // every CTA gets the whole row
-    } else {
-      out[(size_t)b * nq * hd + (size_t)(kvh * G + g) * hd + (e % hd)] = o;
-    }
+    out[(size_t)b * nq * hd + (size_t)(kvh * G + g) * hd + (e % hd)] = from_f<T>(a / L);
   }
-  if (OPROJ) asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's part of the shard has landed
-  cluster.sync();  // nobody leaves while a peer may still read its shared memory (att_s and the shard are complete)
-  if (OPROJ) {
-    // o_proj partial of this rank for rows [rank * rows_per, +rows_per): one warp per row, lanes along K as gemv_res does
-    const uint32_t seq = tp_seq(ex);
-    for (int r = wid; r < rows_per; r += DC_WARPS) {
-      float acc = 0.f;
-      for (int k = lane * V; k < k_o; k += 32 * V) {
-        float wf[V];
-        unpack<T>(*reinterpret_cast<const uint4*>(w_s + (size_t)r * k_o + k), wf);
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc = fmaf(wf[i], att_s[k + i], acc);
-      }
-      acc = warp_sum(acc);          // every lane holds the sum: lane p stores it into rank p's buffer (one instruction per row)
-      if (lane < ex.tp)
-        tp_store_word(tp_slot(ex, lane, seq, ex.rank), (long long)b * d_out + rank * rows_per + r, acc, seq);
-    }
-  }
+  cluster.sync();  // nobody leaves while a peer may still read its shared memory
 }
 
-template <typename T, int G, int NCH, int DC_NS, bool OPROJ = false>
+template <typename T, int G, int NCH, int DC_NS>
 static int launch_da_ns(void* out, const void* q, const void* k_pool, const void* v_pool, const int32_t* page_table,
                      int pt_stride, int page_size, const int32_t* kv_len, int kv_len_add, int B, int nq, int nkv,
-                     int hd, float scale_div, Prefetch pf, cudaStream_t st, const void* w_o = nullptr, int d_out = 0,
-                     TpEx ex = TpEx{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 1, 0, 1}) {
+                     int hd, float scale_div, Prefetch pf, cudaStream_t st) {
   constexpr int TB = NCH == 1 ? 4 : 2;
-  auto kern = decode_attention_cluster_kernel<T, G, NCH, TB, DC_NS, OPROJ>;
+  auto kern = decode_attention_cluster_kernel<T, G, NCH, TB, DC_NS>;
   if (DC_NS > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   // x / 2^k == x * 2^-k exactly (no underflow at these magnitudes): skip the IEEE division routine
-  int exponent = 0;
-  const float scale_mul = (frexpf(scale_div, &exponent) == 0.5f) ? 1.0f / scale_div : 0.f;
-  size_t smem = ((size_t)DC_WARPS * G * hd + 2 * DC_WARPS * G + (size_t)G * hd + 2 * G) * sizeof(float);
-  if (OPROJ) smem = ((smem + 15) & ~(size_t)15) + (size_t)G * hd * sizeof(float) + (size_t)(d_out / DC_NS) * G * hd * sizeof(T);
-  if (smem > 200 * 1024) {
-    set_error("decode_attention: %zu B of shared memory needed", smem);
-    return PG_ERR_INVALID;
-  }
+  int ex = 0;
+  const float scale_mul = (frexpf(scale_div, &ex) == 0.5f) ? 1.0f / scale_div : 0.f;
+  const size_t smem = ((size_t)DC_WARPS * G * hd + 2 * DC_WARPS * G + (size_t)G * hd + 2 * G) * sizeof(float);
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     set_error("decode_attention: cannot reserve %zu B of shared memory", smem);
@@ -374,7 +325,7 @@ static int launch_da_ns(void* out, const void* q, const void* k_pool, const void
   cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (T*)out, (const T*)q, (const T*)k_pool, (const T*)v_pool,
                                      page_table, pt_stride, page_size, kv_len, kv_len_add, nq, nkv, hd, scale_div,
-                                     scale_mul, pf, (const T*)w_o, d_out, ex);
+                                     scale_mul, pf);
   if (e != cudaSuccess) {
     set_error("decode_attention launch: %s", cudaGetErrorString(e));
     cudaGetLastError();
@@ -414,31 +365,6 @@ using namespace pg;
 extern "C" {
 
 long long pg_decode_attention_ws_floats(int, int, int, int) { return 0; }
-
-int pg_decode_attention_oproj(const void* q, const void* k_pool, const void* v_pool, const int32_t* page_table,
-                              int pt_stride, int page_size, const int32_t* kv_len, int kv_len_add, int B, int nq, int hd,
-                              float scale_div, const void* w_o, int d_out, const pg_tp_exchange* ex, int dtype, void* stream) {
-  const Prefetch pf = take_prefetch();
-  PG_REQUIRE(ex && w_o && B > 0 && B <= 9 && (nq == 1 || nq == 2) && d_out % 16 == 0,
-             "decode_attention_oproj: needs a tensor-parallel exchange, 1-2 local heads, batch <= 9 (B=%d nq=%d)", B, nq);
-  const TpEx tex = tp_ex_from(ex);
-  PG_REQUIRE(tex.tp >= 2 && tex.tp <= TP_MAX_RANKS && (long long)B * d_out * 8 <= tex.slot_bytes,
-             "decode_attention_oproj: bad tensor-parallel exchange");
-  cudaStream_t st = (cudaStream_t)stream;
-#define PG_DAO(GG, NCH) \
-  return launch_da_ns<T, GG, NCH, 16, true>(nullptr, q, k_pool, v_pool, page_table, pt_stride, page_size, kv_len, kv_len_add, B, \
-                                            nq, 1, hd, scale_div, pf, st, w_o, d_out, tex)
-  PG_DISPATCH_DTYPE(dtype, T, {
-    constexpr int V = Vec<T>::N;
-    PG_REQUIRE(hd % V == 0 && hd % 4 == 0 && hd <= 64 * V && (nq * hd) % V == 0, "decode_attention_oproj: unsupported head_dim %d", hd);
-    const int nch = (hd + 32 * V - 1) / (32 * V);
-    if (nch == 1) { if (nq == 1) { PG_DAO(1, 1); } PG_DAO(2, 1); }
-    if (nq == 1) { PG_DAO(1, 2); }
-    PG_DAO(2, 2);
-  });
-#undef PG_DAO
-  return PG_OK;
-}
 
 int pg_decode_attention(void* out, const void* q, const void* k_pool, const void* v_pool,
                         const int32_t* page_table, int pt_stride, int page_size, const int32_t* kv_len,

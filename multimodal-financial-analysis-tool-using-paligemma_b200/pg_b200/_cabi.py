@@ -50,7 +50,6 @@ SIGNATURES = {
     "pg_decode_attention_ws_floats": [_i, _i, _i, _i],
     "pg_decode_attention": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _i,
                             _i, _vp],
-    "pg_decode_attention_oproj": [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _vp],
     "pg_gemv_res": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "pg_decode_gateup": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "pg_decode_lmhead": [_vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _vp, _vp, _i, _vp],

@@ -644,16 +644,6 @@ class DecodeState:
             return None
         return fab
 
-    def _attn_oproj_fused(self) -> bool:
-        """Tensor parallel with 1-2 local heads: can the attention cluster also hold its D/16 rows of the o_proj shard in
-        shared memory (pg_decode_attention_oproj)?"""
-        eng, d = self.eng, self.eng.dims
-        if os.environ.get("PG_TP_ATTN_OPROJ", "1") == "0" or d.nkv != 1 or eng.nq_l not in (1, 2) or self.B > 8 or d.D % 16:
-            return False
-        esize = torch.tensor([], dtype=eng.dtype).element_size()
-        scratch = (8 * eng.nq_l * d.hd + 16 * eng.nq_l + eng.nq_l * d.hd + 2 * eng.nq_l + 4) * 4 + eng.nq_l * d.hd * 4
-        return scratch + (d.D // 16) * eng.nq_l * d.hd * esize <= 190 * 1024
-
     def layer_gemv_gen(self, li: int, kv: PagedKV, fab, first: bool):
         """Decoder layer `li` of the GEMV step (batch <= 8).  Residual stream: enters in self.x (`first`) or, tensor
         parallel with the exchange, as self.x2 + the pending down_proj partials; leaves in self.x (no exchange) or as
@@ -680,24 +670,16 @@ class DecodeState:
                        "decode_qkv")
             yield
         self._pf(w["gu"])                                  # attention pulls the head of gate/up
-        if fab is not None and self._attn_oproj_fused():
-            # 1-2 local heads: attention + this rank's o_proj + the exchange producer in one cluster launch
+        cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
+                                         kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, nq, d.nkv, d.hd,
+                                         scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
+                   "decode_attention")
+        yield
+        if fab is not None:
+            # producer -> consumer pairs: the partial sums travel inside the kernels (csrc/tp_exchange.cuh)
             ex_o, ex_d = fab.x(2 * li + 1, stride), fab.x(2 * li + 2, stride)
-            cabi.check(L.pg_decode_attention_oproj(ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table), kv.max_pages,
-                                                   eng.page_size, ptr(kv.kv_len), 1, B, nq, d.hd, scale_div, ptr(w["o"]),
-                                                   d.D, exref(ex_o), dt, st), "decode_attention_oproj")
+            cabi.check(L.pg_gemv_res(None, ptr(self.att), ptr(w["o"]), None, B, d.D, nq * d.hd, exref(ex_o), dt, st), "o_proj")
             yield
-        else:
-            cabi.check(L.pg_decode_attention(ptr(self.att), ptr(self.q), ptr(kp), ptr(vp), ptr(kv.page_table),
-                                             kv.max_pages, eng.page_size, ptr(kv.kv_len), 1, B, nq, d.nkv, d.hd,
-                                             scale_div, ptr(self.ws), ptr(self.counters), eng.max_splits, dt, st),
-                       "decode_attention")
-            yield
-            if fab is not None:
-                # producer -> consumer pairs: the partial sums travel inside the kernels (csrc/tp_exchange.cuh)
-                ex_o, ex_d = fab.x(2 * li + 1, stride), fab.x(2 * li + 2, stride)
-                cabi.check(L.pg_gemv_res(None, ptr(self.att), ptr(w["o"]), None, B, d.D, nq * d.hd, exref(ex_o), dt, st), "o_proj")
-                yield
         if fab is not None:
             cabi.check(L.pg_decode_gateup(ptr(self.g), ptr(x), ptr(w["ln2"]), ptr(w["gu"]), B, d.D, F_l, d.eps,
                                           exref(ex_o), ptr(x2), dt, st), "gateup")

@@ -529,45 +529,3 @@ def test_gemm_tcgen05_prompt_rows_swapped_pairs(dtype, M, N, K, epi):
     cabi.check(cabi.lib().pg_gemm(ref.data_ptr(), ad.data_ptr(), wd.data_ptr(), None, rd.data_ptr(), M, N, K, K, K, N, N, 0,
                                   code, 0, 1, cabi.DTYPE_CODE[dtype], st()))
     close(out, ref.cpu(), dtype)
-
-
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("B,T,nq,hd,D", [(1, 300, 1, 256, 2048), (2, 70, 2, 256, 2048), (3, 33, 2, 32, 128), (1, 20, 1, 32, 128)])
-def test_decode_attention_with_fused_oproj_pushes_the_partials(dtype, B, T, nq, hd, D):
-    """Tensor parallel with 1-2 local heads: attention + this rank's o_proj + the exchange producer in ONE cluster launch
-    (pg_decode_attention_oproj).  The fp32 words it stores into EVERY rank's exchange buffer must equal
-    pg_decode_attention's row times the o_proj shard, with the sequence number of the exchange as flag."""
-    from pg_b200.dist import Fabric
-    from pg_b200._cabi import exref
-    if dtype == torch.float32 and (D // 16) * nq * hd * 4 > 150 * 1024:
-        pytest.skip("the fp32 shard rows do not fit the cluster's shared memory (the engine keeps the two-launch path)")
-    nkv, tp, rank = 1, 2, 1
-    k, v, kp, vp, pt, npg, page = _paged(B, T, nkv, hd, dtype)
-    q = gen(B, nq, 1, hd, seed=9, dtype=dtype)
-    qd = dev(q.transpose(1, 2).reshape(B, nq * hd))
-    kvl = torch.full((B,), T - 1, dtype=torch.int32, device="cuda")
-    att = torch.empty((B, nq * hd), dtype=dtype, device="cuda")
-    ws, cnt = torch.zeros(1, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
-    cabi.check(cabi.lib().pg_decode_attention(att.data_ptr(), qd.data_ptr(), kp.data_ptr(), vp.data_ptr(), pt.data_ptr(), npg,
-                                              page, kvl.data_ptr(), 1, B, nq, nkv, hd, float(math.sqrt(hd)), ws.data_ptr(),
-                                              cnt.data_ptr(), 16, cabi.DTYPE_CODE[dtype], st()))
-    w_o = gen(D, nq * hd, seed=21, scale=1.0 / math.sqrt(nq * hd), dtype=dtype)
-    fabs = Fabric.emulated(tp, D, "cuda")
-    for f in fabs:
-        cabi.check(cabi.lib().pg_tp_begin_step(f.epoch.data_ptr(), st()))
-    index, stride = 3, 8
-    ex = fabs[rank].x(index, stride)
-    cabi.check(cabi.lib().pg_decode_attention_oproj(qd.data_ptr(), kp.data_ptr(), vp.data_ptr(), pt.data_ptr(), npg, page,
-                                                    kvl.data_ptr(), 1, B, nq, hd, float(math.sqrt(hd)), dev(w_o).data_ptr(), D,
-                                                    exref(ex), cabi.DTYPE_CODE[dtype], st()))
-    torch.cuda.synchronize()
-    want = F.linear(att.float().cpu(), w_o.float())                 # fp32 accumulation of the rounded attention row
-    seq = 1 * stride + index
-    for f in fabs:                                                  # the partial landed in every rank's buffer, slot (parity, rank)
-        off = ((seq & 1) * tp + rank) * f.x_slot
-        words = f.buf[off: off + B * D * 8].view(torch.int32).view(B * D, 2).cpu()
-        assert bool((words[:, 1] == seq).all())
-        got = words[:, 0].contiguous().view(torch.float32).view(B, D)
-        torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5 * float(want.abs().max()))
-        other = ((seq & 1) * tp + (1 - rank)) * f.x_slot
-        assert int(f.buf[other: other + B * D * 8].view(torch.int32).abs().sum()) == 0   # nobody else's slot was touched

@@ -123,13 +123,6 @@ def main():
             for li, w in enumerate(eng.t_layers):
                 L.pg_gemv_res(None, ds.att.data_ptr(), w["o"].data_ptr(), None, B, d.D, nq * d.hd, exref(ex), dt, st)
         rec("o_proj_push", oproj_push, e * d.D * nq * d.hd)
-        if ds._attn_oproj_fused():
-            def attn_oproj():
-                for li, w in enumerate(eng.t_layers):
-                    L.pg_decode_attention_oproj(ds.q.data_ptr(), eng.k_pool[li].data_ptr(), eng.v_pool[li].data_ptr(),
-                                                kv.page_table.data_ptr(), kv.max_pages, eng.page_size, kv.kv_len.data_ptr(), 1, B,
-                                                nq, d.hd, 16.0, w["o"].data_ptr(), d.D, exref(ex), dt, st)
-            rec("attention+o_proj fused", attn_oproj, e * d.D * nq * d.hd)
         res["tp"] = tp_size
         print(json.dumps(res))
         return
