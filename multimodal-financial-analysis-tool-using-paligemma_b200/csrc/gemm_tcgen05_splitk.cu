@@ -205,9 +205,25 @@ int gemm_tc_splitk_factor(int M, int N, int K, int epi, int* bn_out) {
   // 6 TB/s.  With several m-tiles (260-token prefill) the GEMM is L2->SM bound and splitting measured 6 % slower.
   static const int mode = env_int("PG_SPLITK", -1);
   if (mode == 0 || epi == PG_EPI_GEGLU) return 0;
-  if (mode < 0 && M > tc::SK_BM) return 0;
+  const int kb = cdiv(K, tc::SK_BK);
+  if (mode < 0 && M > tc::SK_BM) {
+    // Exception: SigLIP at batch 1 (256 patch rows): out_proj and fc2 are 256 x 1152 outputs -- 36 CTAs of 64 columns,
+    // fc2 with 68 serial K blocks each (28 us for a 10 MB matrix; ncu: 36 SMs active, ~640 cycles per K block).
+    // Clusters must fit ONE wave: at most 4 clusters of 4 per GPC (36 clusters of 4 took two waves and 29 us).
+    // Measured, SigLIP encode of one image: unsplit 2.009 ms; S=2 x 64 columns 1.803; S=4 x 128 columns 1.855; S=2 x
+    // 128 columns 1.909; also splitting out_proj (20 K blocks) 1.935 -- that one sits on the launch floor already.
+    static const int small_s = env_int("PG_SPLITK_SMALL_S", 2), small_bn = env_int("PG_SPLITK_SMALL_BN", 64);
+    static const int small_kb = env_int("PG_SPLITK_SMALL_KB", 32);
+    if (M > 2 * tc::SK_BM || N > 2048 || kb < small_kb || small_s < 2) return 0;
+    const int tiles = cdiv(M, tc::SK_BM) * cdiv(N, small_bn);
+    int s = small_s >= 4 ? 4 : 2;
+    while (s >= 2 && (kb / s < 8 || tiles * s > (s == 4 ? 112 : 144))) s /= 2;
+    if (s < 2) return 0;
+    *bn_out = small_bn;
+    return s;
+  }
   const int bn = N <= 4096 ? 64 : 128;
-  const int tiles = cdiv(M, tc::SK_BM) * cdiv(N, bn), kb = cdiv(K, tc::SK_BK);
+  const int tiles = cdiv(M, tc::SK_BM) * cdiv(N, bn);
   if (tiles >= 120) return 0;
   int s = (tiles * 4 <= 320 && kb >= 32) ? 4 : ((kb >= 16) ? 2 : 0);
   *bn_out = bn;
