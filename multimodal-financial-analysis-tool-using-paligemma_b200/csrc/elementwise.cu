@@ -320,7 +320,7 @@ __global__ void step_advance_kernel(int64_t* next_ids, int64_t* history, int his
     if (positions) positions[b] += 1;
     keys[b] = 0ull;
   }
-  if (b == 0 && step_counter) *step_counter = step + 1;
+  if (b == 0 && step_counter) *step_counter = (int)((unsigned)step + 1u);   // wraps like the ring index above
 }
 
 // One launch at the head of an API-driven decode step: token ids and positions into the graph's static buffers,

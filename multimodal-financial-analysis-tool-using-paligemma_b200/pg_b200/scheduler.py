@@ -211,10 +211,11 @@ class ContinuousBatcher:
             self.ds.ids.index_fill_(0, idx, 1)
         self.ds.run_steps(self.kv, n, sample=self.sample)
         self.steps_run += n
-        cols = (torch.arange(n, device=self.eng.device) + self._hist_pos) % self.ds.max_hist   # ring buffer
+        # ring buffer; the device counter is a 32-bit integer that wraps, so its host mirror wraps with it
+        cols = ((torch.arange(n, device=self.eng.device) + self._hist_pos) & 0xFFFFFFFF) % self.ds.max_hist
         hist = self.ds.history[:, cols].cpu()               # one read-back per chunk
         self.eng.check_errors()                             # the read-back synchronised: bad ids raise here
-        self._hist_pos += n
+        self._hist_pos = (self._hist_pos + n) & 0xFFFFFFFF
         for slot, r in list(self.running.items()):
             self.kv.host_len[slot] += n
             for t in hist[slot].tolist():
