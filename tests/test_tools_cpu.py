@@ -37,3 +37,32 @@ def test_visualize_results_writes_the_four_figures(tmp_path):
         assert len(doc.getElementsByTagName("polyline")) >= 2          # one curve per (mode, GPU count)
     speed = (out / "fig4_speedup.svg").read_text()
     assert "1 GPU" in speed and "8 GPUs" in speed
+
+
+def test_ncu_compact_feeds_the_bench_traffic_reader(tmp_path, monkeypatch):
+    """tools/ncu_compact.py keeps the columns bench.py::ncu_traffic_per_launch reads (dram read + write per launch of
+    the dominant decode kernel) out of a wide `ncu --page raw --csv` export."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, ROOT)
+    import csv
+    import io
+    import ncu_compact
+    head = ["ID", "Kernel Name", "junk__metric.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__time_duration.sum", "launch__grid_size", "x1", "x2", "x3", "x4"]
+    units = ["", "", "", "Mbyte", "Mbyte", "us", "", "", "", "", ""]
+    rows = [head, units,
+            ["0", "void pg::decode_gateup_kernel<__nv_bfloat16, 1, 0>(...)", "7", "134.25", "3.5", "27.1", "444", "", "", "", ""],
+            ["1", "void pg::decode_gateup_kernel<__nv_bfloat16, 1, 0>(...)", "7", "134.25", "4.5", "26.9", "444", "", "", "", ""],
+            ["2", "void pg::gemv_res_kernel<__nv_bfloat16, 1, 4, 0>(...)", "7", "67.16", "0.4", "20.9", "888", "", "", "", ""]]
+    out = ncu_compact.compact(rows)
+    assert out[0][:3] == ["Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum"] and "junk__metric.sum" not in out[0]
+    assert out[1][1] == "Mbyte" and len(out) == 5
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    buf = io.StringIO()
+    csv.writer(buf, lineterminator="\n").writerows(out)
+    (prof / "r02_ncu_full_gateup.csv").write_text(buf.getvalue())
+    import bench
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    traffic, source = bench.ncu_traffic_per_launch()
+    assert abs(traffic - (134.25 + 4.0) * 1e6) < 1.0 and "2 launches" in source
