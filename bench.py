@@ -274,7 +274,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count(), "torch_threads": cores},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------- GPU measurements
@@ -656,6 +656,26 @@ def run_ours(args, rank, world, local):
         "batched_decode": batched,
         "setup_s": {"synthetic_weights": round(t_weights, 1)},
     }
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE line, the JSON record: whatever else a library writes to file descriptor 1 during the
+    run (NCCL's version banner under torchrun, for one) is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
     print(json.dumps(line), flush=True)
 
 
@@ -676,6 +696,7 @@ def main():
                          "collective).  Both are measured in every N > 1 run; the other one is reported beside the headline.")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    quiet_stdout()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))

@@ -66,3 +66,13 @@ def test_ncu_compact_feeds_the_bench_traffic_reader(tmp_path, monkeypatch):
     monkeypatch.setattr(bench, "ROOT", str(tmp_path))
     traffic, source = bench.ncu_traffic_per_launch()
     assert abs(traffic - (134.25 + 4.0) * 1e6) < 1.0 and "2 launches" in source
+
+
+def test_bench_stdout_carries_only_the_json_line():
+    """bench.py's contract: ONE JSON line on stdout.  Anything a library writes to file descriptor 1 during the run
+    (NCCL prints its version banner there under torchrun) must land on stderr instead."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.quiet_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('chatter'); bench.emit({'metric': 'x', 'value': 1.0})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
+    assert r.stdout.strip().splitlines() == [json.dumps({"metric": "x", "value": 1.0})]
+    assert "NCCL version" in r.stderr and "chatter" in r.stderr
